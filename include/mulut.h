@@ -1,0 +1,146 @@
+/*
+ * mulut.h — C ABI of libmulut_b200.so: the B200-native (sm_100a) replacement for
+ * MuLUT's LUT-retrieval hot path.  Plain pointers and sizes only; no torch or
+ * numpy types cross this boundary.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every function returns MULUT_OK (0) or a negative MULUT_E_* code;
+ *     mulut_last_error() returns a thread-local, human-readable message.
+ *   - "d_" pointers are device pointers on the handle's device, "h_" pointers
+ *     are host pointers.  All buffers are caller-owned; the library owns only
+ *     its LUT replica and a reusable workspace inside the handle.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *     Calls are asynchronous on that stream unless stated otherwise.
+ *   - LUT tables use the reference's on-disk layout unchanged: int8, C order,
+ *     (L^4, 1) for non-last stages and (L^4, scale^2) for the last stage,
+ *     L = 2^(8-interval)+1, row = a*L^3 + b*L^2 + c*L + d, column = u*scale+v
+ *     (sr/2_transfer_to_lut.py:12-42, sr/4_test_lut.py:61-63,323-333).
+ */
+#ifndef MULUT_B200_H
+#define MULUT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MULUT_OK            0
+#define MULUT_E_BAD_MODE   -1   /* reference: ValueError("Mode {} not implemented.") sr/4_test_lut.py:52-54 */
+#define MULUT_E_BAD_ARG    -2   /* null pointer / bad shape / bad scale / bad interval */
+#define MULUT_E_CUDA       -3   /* a CUDA runtime call failed (see mulut_last_error) */
+#define MULUT_E_NOMEM      -4
+#define MULUT_E_LUT_SMALL  -5   /* reference: numpy IndexError when a LUT has < L^4 rows */
+
+#define MULUT_MAX_MODES     8
+#define MULUT_MAX_STAGES    8
+
+typedef struct mulut_handle_s *mulut_handle_t;
+
+/* Kernel selection for mulut_sr_infer_u8 (parity tests run all of them). */
+#define MULUT_KERNEL_AUTO     (-1)  /* fastest applicable */
+#define MULUT_KERNEL_GENERIC    0   /* any modes/scale/interval/C; LUTs gathered vertex-major from L2 */
+#define MULUT_KERNEL_TILED      1   /* interval 4: smem-resident stage-1 LUTs, cell-major last-stage LUTs */
+
+int mulut_version(void);
+const char *mulut_last_error(void);
+
+/*
+ * Replaces the LUT loading block of sr/4_test_lut.py:323-333 (the caller still
+ * reads the .npy files with the reference's naming rule).  Uploads the tables
+ * to `device`, builds the device-side re-layouts and pins them in L2
+ * (cudaAccessPolicyWindow on the streams used by *_host).
+ *   modes      NUL-terminated string over {s,d,y}, e.g. "sdy"  (--modes)
+ *   host_luts  stage-major, mode-minor: host_luts[s*strlen(modes)+m]
+ *   lut_rows   rows of every table (must be >= L^4), normally 83521
+ */
+int mulut_create(mulut_handle_t *handle, int device, int stages, const char *modes,
+                 int scale, int interval, const int8_t *const *host_luts, int lut_rows);
+int mulut_destroy(mulut_handle_t handle);
+int mulut_set_kernel(mulut_handle_t handle, int kernel);
+/* Pre-size the workspace (stage intermediates, staging buffers) so that the
+ * hot call allocates nothing. Optional: the hot calls grow it on demand. */
+int mulut_reserve(mulut_handle_t handle, int N, int H, int W, int C);
+
+/*
+ * Replaces the whole per-image loop of eltr._worker, sr/4_test_lut.py:279-306
+ * (stages x modes x 4 rotations of FourSimplexInterpFaster + epilogue).
+ *   d_in   uint8 (N, H, W, C) interleaved (PIL / HWC order)
+ *   d_out  uint8 (N, H*scale, W*scale, C)
+ * Bit-exact with the reference's numpy path.
+ */
+int mulut_sr_infer_u8(mulut_handle_t handle, const uint8_t *d_in, uint8_t *d_out,
+                      int N, int H, int W, int C, void *stream);
+
+/* Same, from/to HOST buffers (pinned memory recommended: mulut_host_alloc):
+ * frames are pipelined H2D -> kernels -> D2H over internal streams.
+ * Synchronous: returns when h_out is complete. */
+int mulut_sr_infer_u8_host(mulut_handle_t handle, const uint8_t *h_in, uint8_t *h_out,
+                           int N, int H, int W, int C);
+
+/* number of kernel launches issued by this handle since creation */
+long long mulut_launch_count(mulut_handle_t handle);
+
+/*
+ * Signature-compatible single pass: FourSimplexInterpFaster(weight, img_in, h, w,
+ * interval, rot, upscale, mode), sr/4_test_lut.py:14-237.
+ *   d_weight  float32 (n_rows, upscale^2)  (int8 values stored as float32, :333)
+ *   d_img_in  float32 (C, h+p, w+p), already rotated and edge padded (p = 1 for s, 2 for d,y)
+ *   d_out     float64 (C, h*up, w*up) if rot is even else (C, w*up, h*up): np.rot90(out, rot, [1,2]) / q
+ */
+int mulut_interp_pass_f64(const float *d_weight, int n_rows, const float *d_img_in,
+                          int C, int h, int w, int interval, int rot, int upscale,
+                          char mode, double *d_out, void *stream);
+
+/*
+ * MuLUT.InterpTorchBatch forward, sr/model.py:69-287.
+ *   d_weight  float32 (n_rows, up^2), the raw nn.Parameter (quantised on the fly:
+ *             clamp(round_half_even(w*127), -127, 127), model.py:74-76)
+ *   d_img_in  float32 (B, C, h+bd, w+bd);   d_out float32 (B, C, h*up, w*up)
+ */
+int mulut_interp_fwd_f32(const float *d_weight, int n_rows, int up, char mode,
+                         const float *d_img_in, int B, int C, int h, int w, int bd,
+                         int interval, float *d_out, void *stream);
+/*
+ * Backward of the above (what torch autograd derives for model.py:69-287).
+ *   d_grad_out     float32 (B, C, h*up, w*up)
+ *   d_grad_weight  float32 (n_rows, up^2), ACCUMULATED INTO (+=); may be NULL
+ *   d_grad_img_in  float32 (B, C, h+bd, w+bd), ACCUMULATED INTO (+=); may be NULL
+ * Ties between LSB fractions are broken "higher tap index first", which is what
+ * the reference's 24 strict-inequality cases resolve to.
+ */
+int mulut_interp_bwd_f32(const float *d_weight, int n_rows, int up, char mode,
+                         const float *d_img_in, int B, int C, int h, int w, int bd,
+                         int interval, const float *d_grad_out,
+                         float *d_grad_weight, float *d_grad_img_in, void *stream);
+
+/* Pinned host memory for the *_host entry points. */
+void *mulut_host_alloc(size_t bytes);
+int mulut_host_free(void *p);
+
+/*
+ * L2/L1/shared-memory gather micro-benchmark: the measured denominator of the
+ * gather roofline (no datasheet figure exists for it).
+ *   variant      see MULUT_GB_* below
+ *   table_bytes  size of the random-access table
+ *   out[0] = gathers per second (one gather = one LUT vertex / cell fetch)
+ *   out[1] = useful bytes per second, out[2] = seconds per launch
+ */
+#define MULUT_GB_LDG_U8        0   /* 1-byte loads, one lane per random address              */
+#define MULUT_GB_LDG_U32       1   /* 4-byte loads, one lane per random address              */
+#define MULUT_GB_LDG_U128      2   /* 16-byte loads, one lane per random address             */
+#define MULUT_GB_QUAD_CELL64   3   /* 4 lanes x 16 B cover one random 64-byte cell           */
+#define MULUT_GB_LDS_U8        4   /* 1-byte loads from a shared-memory table                */
+#define MULUT_GB_PAIR_CELL64   5   /* 2 lanes x 32 B (256-bit loads) cover one 64-byte cell  */
+#define MULUT_GB_OCT_CELL128   6   /* 8 lanes x 16 B cover one random 128-byte line          */
+#define MULUT_GB_CPASYNC_CELL64 7  /* 4 lanes x cp.async 16 B stage a cell in smem + 5 LDS   */
+#define MULUT_GB_LDS_U32       8   /* 4-byte loads from a shared-memory table                */
+int mulut_gather_bench(int device, int variant, size_t table_bytes, int iters_per_thread,
+                       int blocks_per_sm, int threads_per_block, int repeats, double *out3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MULUT_B200_H */

@@ -1,0 +1,70 @@
+"""Builds libmulut_b200.so (in-tree) with nvcc for sm_100a.
+
+    python -m mulut_b200.build [--force] [--verbose]
+
+The shared library is the product's only compute path; there is no CPU
+fallback.  The build needs no GPU (nvcc cross-compiles).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+OBJ_DIR = os.path.join(_HERE, "csrc", "build")
+LIB_PATH = os.path.join(_HERE, "libmulut_b200.so")
+SOURCES = ["capi.cu", "infer_generic.cu", "infer_tiled.cu", "interp_f32.cu", "gather_bench.cu"]
+HEADERS = ["common.cuh", "infer.cuh", os.path.join("..", "..", "include", "mulut.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isfile(cand) or cand == "nvcc"):
+            return cand
+    return "nvcc"
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.isfile(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdrs = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS] + [os.path.abspath(__file__)]
+    objs = []
+    nvcc = _nvcc()
+    env = dict(os.environ)
+    # the image's CC/CXX wrappers are fine for host code; let nvcc pick its default host compiler
+    procs = []
+    for src in SOURCES:
+        sp = os.path.join(CSRC, src)
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _stale(obj, [sp] + hdrs):
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", obj]
+            procs.append((src, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            sys.stderr.write("== nvcc {} ==\n{}\n".format(src, out.decode(errors="replace")))
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed (see log above)")
+    if force or procs or _stale(LIB_PATH, objs):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
+        subprocess.check_call(cmd, env=env)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,351 @@
+// C ABI of libmulut_b200.so: handle management and the inference entry points
+// (include/mulut.h).  The floating-point entry points live in interp_f32.cu, the
+// micro-benchmark in gather_bench.cu.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "infer.cuh"
+
+namespace mulut {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return e == cudaErrorMemoryAllocation ? MULUT_E_NOMEM : MULUT_E_CUDA;
+}
+
+constexpr int HOST_LANES = 3;      // frames in flight on the host path
+
+struct Workspace {
+    uint8_t *img[2] = {nullptr, nullptr};   // stage intermediates (ping-pong)
+    size_t img_bytes = 0;
+    int16_t *partial = nullptr;             // per-mode int16 planes of the smem-LUT kernel
+    size_t partial_bytes = 0;
+};
+
+}  // namespace mulut
+
+using namespace mulut;
+
+struct mulut_handle_s {
+    int device = 0, stages = 0, n_modes = 0, scale = 0, interval = 0, lut_rows = 0, num_sms = 0;
+    char modes[MULUT_MAX_MODES + 1] = {0};
+    int kernel = MULUT_KERNEL_AUTO;
+    uint8_t *d_luts = nullptr;              // one allocation: reference-layout tables, then re-layouts
+    size_t lut_bytes = 0;
+    const int8_t *lut[MULUT_MAX_STAGES][MULUT_MAX_MODES] = {};
+    const uint8_t *lut_alt[MULUT_MAX_STAGES][MULUT_MAX_MODES] = {};
+    TapTable taps;
+    Workspace ws[1 + HOST_LANES];           // [0] device API, [1..] host-path lanes
+    cudaStream_t lane_stream[HOST_LANES] = {};
+    uint8_t *lane_in[HOST_LANES] = {}, *lane_out[HOST_LANES] = {};
+    size_t lane_in_bytes = 0, lane_out_bytes = 0;
+    long long launches = 0;
+};
+
+static int ws_reserve(Workspace &w, int stages, int n_modes, size_t frame_samples, bool want_partial)
+{
+    if (stages > 1 && w.img_bytes < frame_samples) {
+        for (int i = 0; i < 2; ++i) { cudaFree(w.img[i]); w.img[i] = nullptr; }
+        w.img_bytes = 0;
+        const int nbuf = stages > 2 ? 2 : 1;
+        for (int i = 0; i < nbuf; ++i) MULUT_CUDA(cudaMalloc(&w.img[i], frame_samples));
+        if (nbuf == 1) w.img[1] = nullptr;
+        w.img_bytes = frame_samples;
+    }
+    const size_t need = want_partial ? frame_samples * n_modes * sizeof(int16_t) : 0;
+    if (w.partial_bytes < need) {
+        cudaFree(w.partial); w.partial = nullptr; w.partial_bytes = 0;
+        MULUT_CUDA(cudaMalloc(&w.partial, need));
+        w.partial_bytes = need;
+    }
+    return MULUT_OK;
+}
+
+static void ws_free(Workspace &w)
+{
+    cudaFree(w.img[0]); cudaFree(w.img[1]); cudaFree(w.partial);
+    w = Workspace();
+}
+
+static bool uses_tiled(const mulut_handle_s *h, int up, int C)
+{
+    if (h->kernel == MULUT_KERNEL_GENERIC) return false;
+    return tiled_supported(up, h->interval, h->n_modes) && (C >= 1 && C <= 4);
+}
+
+static int run_stages(mulut_handle_s *h, Workspace &w, const uint8_t *d_in, uint8_t *d_out, int N, int H, int W,
+                      int C, cudaStream_t stream)
+{
+    const size_t samples = (size_t)N * H * W * C;
+    if (samples == 0) return MULUT_OK;
+    bool want_partial = false;
+    for (int s = 0; s < h->stages; ++s) {
+        const bool last = s + 1 == h->stages;
+        const int up = last ? h->scale : 1;
+        if (up == 1 && uses_tiled(h, up, C)) want_partial = true;
+    }
+    int rc = ws_reserve(w, h->stages, h->n_modes, samples, want_partial);
+    if (rc) return rc;
+
+    const uint8_t *cur = d_in;
+    for (int s = 0; s < h->stages; ++s) {
+        const bool last = s + 1 == h->stages;
+        const int up = last ? h->scale : 1;
+        StageArgs a;
+        memset(&a, 0, sizeof a);
+        a.in = cur;
+        a.out = last ? d_out : w.img[(h->stages > 2) ? (s & 1) : 0];
+        a.N = N; a.H = H; a.W = W; a.C = C;
+        a.n_modes = h->n_modes; a.interval = h->interval; a.last = last ? 1 : 0; a.num_sms = h->num_sms;
+        for (int m = 0; m < h->n_modes; ++m) {
+            a.lut[m] = h->lut[s][m];
+            a.lut_alt[m] = h->lut_alt[s][m];
+            a.modes[m] = h->modes[m];
+        }
+        a.taps = h->taps;
+        int done = 1;
+        if (uses_tiled(h, up, C)) {
+            int launches = 0;
+            done = launch_stage_tiled_ws(a, up, w.partial, stream, &launches);
+            if (done < 0) return done;
+            h->launches += launches;
+        }
+        if (done == 1) {
+            rc = launch_stage_generic(a, up, stream);
+            if (rc) return rc;
+            h->launches += 1;
+        }
+        cur = a.out;
+    }
+    return MULUT_OK;
+}
+
+extern "C" {
+
+int mulut_version(void) { return 100; }
+const char *mulut_last_error(void) { return g_err; }
+
+int mulut_create(mulut_handle_t *handle, int device, int stages, const char *modes, int scale, int interval,
+                 const int8_t *const *host_luts, int lut_rows)
+{
+    if (!handle || !modes || !host_luts) { set_error("mulut_create: null argument"); return MULUT_E_BAD_ARG; }
+    *handle = nullptr;
+    const int n_modes = (int)strlen(modes);
+    if (stages < 1 || stages > MULUT_MAX_STAGES || n_modes < 1 || n_modes > MULUT_MAX_MODES || scale < 1 ||
+        scale > 4 || interval < 1 || interval > 7) {
+        set_error("mulut_create: stages=%d modes='%s' scale=%d interval=%d out of range", stages, modes, scale,
+                  interval);
+        return MULUT_E_BAD_ARG;
+    }
+    mulut_handle_s *h = new mulut_handle_s();
+    if (!build_tap_table(modes, n_modes, &h->taps)) {
+        for (int m = 0; m < n_modes; ++m) {
+            int dy[4], dx[4];
+            if (!mode_taps(modes[m], dy, dx)) { set_error("Mode %c not implemented.", modes[m]); break; }
+        }
+        delete h;
+        return MULUT_E_BAD_MODE;
+    }
+    const long long L = (1 << (8 - interval)) + 1;
+    if ((long long)lut_rows < L * L * L * L) {
+        set_error("LUT too small: need %lld rows, have %d", L * L * L * L, lut_rows);
+        delete h;
+        return MULUT_E_LUT_SMALL;
+    }
+    for (int i = 0; i < stages * n_modes; ++i)
+        if (!host_luts[i]) { set_error("mulut_create: host_luts[%d] is null", i); delete h; return MULUT_E_BAD_ARG; }
+
+    h->device = device; h->stages = stages; h->n_modes = n_modes; h->scale = scale; h->interval = interval;
+    h->lut_rows = lut_rows;
+    memcpy(h->modes, modes, n_modes);
+
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__); }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaGetDeviceProperties", __FILE__, __LINE__); }
+    h->num_sms = prop.multiProcessorCount;
+
+    // one contiguous allocation: [reference-layout tables | re-layouts], 256-byte aligned pieces
+    auto align256 = [](size_t b) { return (b + 255) / 256 * 256; };
+    size_t off = 0, lut_off[MULUT_MAX_STAGES][MULUT_MAX_MODES], alt_off[MULUT_MAX_STAGES][MULUT_MAX_MODES];
+    for (int s = 0; s < stages; ++s) {
+        const int up2 = (s + 1 == stages) ? scale * scale : 1;
+        for (int m = 0; m < n_modes; ++m) { lut_off[s][m] = off; off += align256((size_t)lut_rows * up2); }
+    }
+    for (int s = 0; s < stages; ++s) {
+        const int up = (s + 1 == stages) ? scale : 1;
+        const size_t ab = interval == 4 ? cell_major_bytes(up) : 0;
+        for (int m = 0; m < n_modes; ++m) { alt_off[s][m] = off; off += align256(ab); }
+    }
+    h->lut_bytes = off;
+    e = cudaMalloc(&h->d_luts, off);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(luts)", __FILE__, __LINE__); }
+    int rc = MULUT_OK;
+    for (int s = 0; s < stages && !rc; ++s) {
+        const int up = (s + 1 == stages) ? scale : 1;
+        const int up2 = up * up;
+        for (int m = 0; m < n_modes && !rc; ++m) {
+            int8_t *dst = reinterpret_cast<int8_t *>(h->d_luts + lut_off[s][m]);
+            e = cudaMemcpy(dst, host_luts[s * n_modes + m], (size_t)lut_rows * up2, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpy(lut)", __FILE__, __LINE__); break; }
+            h->lut[s][m] = dst;
+            if (interval == 4 && cell_major_bytes(up) > 0) {
+                uint8_t *alt = h->d_luts + alt_off[s][m];
+                rc = build_cell_major(dst, alt, up, 0);
+                h->lut_alt[s][m] = alt;
+            }
+        }
+    }
+    if (!rc) {
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaDeviceSynchronize", __FILE__, __LINE__);
+    }
+    if (rc) { cudaFree(h->d_luts); delete h; return rc; }
+
+    // L2 residency: keep the LUT allocation in the persisting carve-out for the
+    // library's own streams (the tables are 1.3-14 MB; L2 is 126 MB).
+    const char *env = getenv("MULUT_L2_PERSIST");
+    const bool persist = !(env && env[0] == '0');
+    for (int i = 0; i < HOST_LANES; ++i) {
+        e = cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking);
+        if (e != cudaSuccess) { mulut_destroy(h); return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+    }
+    if (persist && prop.persistingL2CacheMaxSize > 0) {
+        size_t want = h->lut_bytes < (size_t)prop.persistingL2CacheMaxSize ? h->lut_bytes
+                                                                           : (size_t)prop.persistingL2CacheMaxSize;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof attr);
+            attr.accessPolicyWindow.base_ptr = h->d_luts;
+            size_t win = h->lut_bytes;
+            if (win > (size_t)prop.accessPolicyMaxWindowSize) win = (size_t)prop.accessPolicyMaxWindowSize;
+            attr.accessPolicyWindow.num_bytes = win;
+            attr.accessPolicyWindow.hitRatio = 1.0f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            for (int i = 0; i < HOST_LANES; ++i)
+                cudaStreamSetAttribute(h->lane_stream[i], cudaStreamAttributeAccessPolicyWindow, &attr);
+        }
+        cudaGetLastError();   // residency is best-effort
+    }
+    *handle = h;
+    return MULUT_OK;
+}
+
+int mulut_destroy(mulut_handle_t h)
+{
+    if (!h) return MULUT_OK;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < HOST_LANES; ++i) {
+        if (h->lane_stream[i]) { cudaStreamSynchronize(h->lane_stream[i]); cudaStreamDestroy(h->lane_stream[i]); }
+        cudaFree(h->lane_in[i]);
+        cudaFree(h->lane_out[i]);
+    }
+    for (auto &w : h->ws) ws_free(w);
+    cudaFree(h->d_luts);
+    delete h;
+    return MULUT_OK;
+}
+
+int mulut_set_kernel(mulut_handle_t h, int kernel)
+{
+    if (!h || kernel < MULUT_KERNEL_AUTO || kernel > MULUT_KERNEL_TILED) {
+        set_error("mulut_set_kernel: bad argument");
+        return MULUT_E_BAD_ARG;
+    }
+    h->kernel = kernel;
+    return MULUT_OK;
+}
+
+long long mulut_launch_count(mulut_handle_t h) { return h ? h->launches : 0; }
+
+static int check_shape(mulut_handle_t h, const void *in, const void *out, int N, int H, int W, int C)
+{
+    if (!h) { set_error("null handle"); return MULUT_E_BAD_ARG; }
+    if (N < 0 || H < 0 || W < 0 || C < 1) { set_error("bad shape N=%d H=%d W=%d C=%d", N, H, W, C); return MULUT_E_BAD_ARG; }
+    if ((size_t)N * H * W * C > 0 && (!in || !out)) { set_error("null image pointer"); return MULUT_E_BAD_ARG; }
+    if ((long long)W * C * h->scale > 0x3fffffffLL || (long long)H * h->scale > 0x3fffffffLL) {
+        set_error("frame too large");
+        return MULUT_E_BAD_ARG;
+    }
+    return MULUT_OK;
+}
+
+int mulut_reserve(mulut_handle_t h, int N, int H, int W, int C)
+{
+    int rc = check_shape(h, (void *)1, (void *)1, N, H, W, C);
+    if (rc) return rc;
+    MULUT_CUDA(cudaSetDevice(h->device));
+    return ws_reserve(h->ws[0], h->stages, h->n_modes, (size_t)N * H * W * C, h->interval == 4);
+}
+
+int mulut_sr_infer_u8(mulut_handle_t h, const uint8_t *d_in, uint8_t *d_out, int N, int H, int W, int C,
+                      void *stream)
+{
+    int rc = check_shape(h, d_in, d_out, N, H, W, C);
+    if (rc) return rc;
+    MULUT_CUDA(cudaSetDevice(h->device));
+    return run_stages(h, h->ws[0], d_in, d_out, N, H, W, C, (cudaStream_t)stream);
+}
+
+int mulut_sr_infer_u8_host(mulut_handle_t h, const uint8_t *h_in, uint8_t *h_out, int N, int H, int W, int C)
+{
+    int rc = check_shape(h, h_in, h_out, N, H, W, C);
+    if (rc) return rc;
+    const size_t fin = (size_t)H * W * C, fout = fin * h->scale * h->scale;
+    if (N == 0 || fin == 0) return MULUT_OK;
+    MULUT_CUDA(cudaSetDevice(h->device));
+    if (h->lane_in_bytes < fin || h->lane_out_bytes < fout) {
+        for (int i = 0; i < HOST_LANES; ++i) {
+            MULUT_CUDA(cudaStreamSynchronize(h->lane_stream[i]));
+            cudaFree(h->lane_in[i]); cudaFree(h->lane_out[i]);
+            h->lane_in[i] = h->lane_out[i] = nullptr;
+        }
+        h->lane_in_bytes = h->lane_out_bytes = 0;
+        for (int i = 0; i < HOST_LANES; ++i) {
+            MULUT_CUDA(cudaMalloc(&h->lane_in[i], fin));
+            MULUT_CUDA(cudaMalloc(&h->lane_out[i], fout));
+        }
+        h->lane_in_bytes = fin; h->lane_out_bytes = fout;
+    }
+    // one frame per lane step: H2D -> stages -> D2H, HOST_LANES frames in flight
+    for (int n = 0; n < N; ++n) {
+        const int lane = n % HOST_LANES;
+        cudaStream_t st = h->lane_stream[lane];
+        MULUT_CUDA(cudaMemcpyAsync(h->lane_in[lane], h_in + (size_t)n * fin, fin, cudaMemcpyHostToDevice, st));
+        rc = run_stages(h, h->ws[1 + lane], h->lane_in[lane], h->lane_out[lane], 1, H, W, C, st);
+        if (rc) return rc;
+        MULUT_CUDA(cudaMemcpyAsync(h_out + (size_t)n * fout, h->lane_out[lane], fout, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < HOST_LANES; ++i) MULUT_CUDA(cudaStreamSynchronize(h->lane_stream[i]));
+    return MULUT_OK;
+}
+
+void *mulut_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__); return nullptr; }
+    return p;
+}
+
+int mulut_host_free(void *p)
+{
+    if (p) MULUT_CUDA(cudaFreeHost(p));
+    return MULUT_OK;
+}
+
+}  // extern "C"

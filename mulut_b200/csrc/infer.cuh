@@ -1,0 +1,36 @@
+// Internal interfaces between capi.cu and the inference kernels.
+#pragma once
+#include "common.cuh"
+
+namespace mulut {
+
+// Arguments of one stage launch (passed by value as a __grid_constant__).
+struct StageArgs {
+    const uint8_t *in;                       // (N, H, W, C) uint8
+    uint8_t *out;                            // (N, H*up, W*up, C) uint8
+    int N, H, W, C;
+    int n_modes;
+    int interval;
+    int last;                                // last stage: up = scale, avg = M, bias 0
+    int num_sms;
+    const int8_t *lut[MULUT_MAX_MODES];      // reference layout: int8 (L^4, up^2)
+    const uint8_t *lut_alt[MULUT_MAX_MODES]; // device re-layout used by the tiled kernels
+    char modes[MULUT_MAX_MODES];
+    TapTable taps;
+};
+
+int launch_stage_generic(const StageArgs &a, int up, cudaStream_t stream);
+
+// Tiled sm_100a kernels (interval 4 only).  Return MULUT_OK, an error, or
+// +1 when the configuration is not covered (caller falls back to generic).
+// partial: workspace of n_modes * N*H*W*C int16 (used when up == 1).
+int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStream_t stream, int *launches);
+bool tiled_supported(int up, int interval, int n_modes);
+
+// Device-side LUT re-layouts (run once at mulut_create).
+//  cell-major: for each of the 16^4 cells, the 16 corner rows laid out so one
+//  aligned 16*up^2-byte block holds everything an interpolation can touch.
+size_t cell_major_bytes(int up);
+int build_cell_major(const int8_t *d_lut_vertex_major, uint8_t *d_cells, int up, cudaStream_t stream);
+
+}  // namespace mulut

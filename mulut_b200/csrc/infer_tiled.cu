@@ -1,0 +1,515 @@
+// Tiled sm_100a inference kernels (interval = 4: q = 16, L = 17).
+//
+//  K1a  stage_smem_kernel      any stage with up = 1.  "Mode-split": every CTA
+//       owns ONE sampling mode for the whole launch and keeps that mode's
+//       83 521-byte int8 LUT in shared memory (staged once by a TMA bulk copy,
+//       cp.async.bulk + mbarrier -> UBLKCP).  It walks halo'd tiles and emits the
+//       int16 partial sum of its 4 rotations per sample.  All five vertex
+//       gathers of an interpolation are LDS.S8 (bank-conflict bound, ~20x the
+//       rate of divergent global gathers).
+//  K1b  combine_kernel         sums the per-mode int16 planes and applies the
+//       stage epilogue (integer round-half-even), writing the uint8 image.
+//  K1c  stage_last2_quad_kernel  last stage, up = 2.  LUTs are re-laid out
+//       cell-major (one aligned 64-byte block per 16^4 cell = all 16 corners x 4
+//       outputs, biased to uint8).  Four adjacent lanes fetch one cell with one
+//       LDG.128 each, so a warp-level gather touches 8 cache lines instead of
+//       32; each lane weights its 4 corners branch-free
+//       (w(S) = relu(min_{i in S} f_i - max_{i not in S} f_i)) and folds them
+//       with dp4a; partial sums meet through warp shuffles.  The 2x2
+//       pixel-shuffle is fused into a shared-memory output tile that is stored
+//       with coalesced 16-byte writes.
+//
+// Arithmetic follows SURVEY.md 8-SPEC (sr/4_test_lut.py:14-237, :279-306).
+#include <cuda/barrier>
+
+#include "common.cuh"
+#include "infer.cuh"
+
+namespace mulut {
+
+constexpr int TWB = 96;                 // tile width in byte columns (multiple of C for C in {1,2,3,4,6})
+constexpr int LUT1_ROWS = 83521;        // 17^4
+constexpr int LUT1_SMEM = 83584;        // padded to a multiple of 128 B
+constexpr uint32_t FULL = 0xffffffffu;
+
+// compile-time tap offsets per (mode, rotation, tap); see common.cuh::build_tap_table
+__host__ __device__ constexpr int tap_off(char mode, int r, int k, bool want_dy)
+{
+    int dy = mode == 's' ? (k >> 1) : mode == 'd' ? 2 * (k >> 1) : (k == 0 ? 0 : k == 1 ? 1 : k == 2 ? 1 : 2);
+    int dx = mode == 's' ? (k & 1) : mode == 'd' ? 2 * (k & 1) : (k == 0 ? 0 : k == 1 ? 1 : k == 2 ? 2 : 1);
+    for (int i = 0; i < r; ++i) { int t = dy; dy = dx; dx = -t; }
+    return want_dy ? dy : dx;
+}
+
+template <int CT> __host__ __device__ constexpr int tile_pitch() { return CT > 0 ? ((TWB + 4 * CT + 3) / 4) * 4 : TWB + 16; }
+
+// smem(r, j) = img[clamp(y0-2+r)][clamp_pixel(X0 - 2C + j)], channel preserved.
+__device__ __forceinline__ void fill_tile(uint8_t *s, int pitch, int rows, int cols,
+                                          const uint8_t *__restrict__ img, int H, int C, int WC,
+                                          int y0, int X0)
+{
+    for (int idx = threadIdx.x; idx < rows * cols; idx += blockDim.x) {
+        const int r = idx / cols, j = idx - r * cols;
+        const int yy = clampi(y0 - 2 + r, 0, H - 1);
+        int xb = X0 - 2 * C + j;
+        if (xb < 0) xb = (xb + 2 * C) % C;
+        else if (xb >= WC) xb = WC - C + (xb % C);
+        s[r * pitch + j] = __ldg(img + (size_t)yy * WC + xb);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1a: shared-memory LUT, one mode per CTA, up = 1
+// ---------------------------------------------------------------------------
+template <char MODE, int CT>
+__device__ __forceinline__ int smem_lut_sample(const uint8_t *__restrict__ sp, int C,
+                                               const int8_t *__restrict__ slut)
+{
+    constexpr int P = tile_pitch<CT>();
+    constexpr uint32_t SB = 20, SM = (1u << SB) - 1u;
+    const int Cc = CT > 0 ? CT : C;
+    const uint32_t t0 = sp[0];
+    int acc = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t t1 = sp[tap_off(MODE, r, 1, true) * P + tap_off(MODE, r, 1, false) * Cc];
+        const uint32_t t2 = sp[tap_off(MODE, r, 2, true) * P + tap_off(MODE, r, 2, false) * Cc];
+        const uint32_t t3 = sp[tap_off(MODE, r, 3, true) * P + tap_off(MODE, r, 3, false) * Cc];
+        const uint32_t v0 = (((t0 >> 4) * 17u + (t1 >> 4)) * 17u + (t2 >> 4)) * 17u + (t3 >> 4);
+        uint32_t k0 = ((t0 & 15u) << SB) | 4913u;
+        uint32_t k1 = ((t1 & 15u) << SB) | 289u;
+        uint32_t k2 = ((t2 & 15u) << SB) | 17u;
+        uint32_t k3 = ((t3 & 15u) << SB) | 1u;
+        sort4_desc(k0, k1, k2, k3);
+        const int f1 = k0 >> SB, f2 = k1 >> SB, f3 = k2 >> SB, f4 = k3 >> SB;
+        // vertex chain: the fraction bits pile up above bit 20 and are masked off
+        const uint32_t v1 = v0 + k0, v2 = v1 + k1, v3 = v2 + k2, v4 = v3 + k3;
+        acc += (16 - f1) * (int)slut[v0];
+        acc += (f1 - f2) * (int)slut[v1 & SM];
+        acc += (f2 - f3) * (int)slut[v2 & SM];
+        acc += (f3 - f4) * (int)slut[v3 & SM];
+        acc += f4 * (int)slut[v4 & SM];
+    }
+    return acc;
+}
+
+constexpr int S1_TH = 32;               // tile rows of K1a
+constexpr int S1_RW = 4;                // row phases (warps = 3 * S1_RW)
+constexpr int S1_THREADS = 96 * S1_RW;
+
+template <int CT>
+__global__ void __launch_bounds__(S1_THREADS, 2)
+stage_smem_kernel(const __grid_constant__ StageArgs a, int16_t *__restrict__ partial, int ctas_per_mode)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    int8_t *slut = reinterpret_cast<int8_t *>(smem_raw);
+    uint8_t *s_in = smem_raw + LUT1_SMEM;
+    __shared__ __align__(8) uint64_t lut_bar;
+
+    constexpr int P = tile_pitch<CT>();
+    const int C = CT > 0 ? CT : a.C;
+    const int WC = a.W * C;
+    const int m = blockIdx.x % a.n_modes;
+    const int slot = blockIdx.x / a.n_modes;
+    const char mode = a.modes[m];
+
+    // --- stage this CTA's LUT into shared memory with one TMA bulk copy ---
+    const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&lut_bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slut);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"((uint32_t)LUT1_SMEM)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+            "l"(a.lut_alt[m]), "r"((uint32_t)LUT1_SMEM), "r"(bar_addr)
+            : "memory");
+    }
+
+    const int tiles_x = (WC + TWB - 1) / TWB;
+    const int tiles_y = (a.H + S1_TH - 1) / S1_TH;
+    const long long n_tiles = (long long)a.N * tiles_y * tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lx = (warp % 3) * 32 + lane;
+    const int rp = warp / 3;
+    const int cols = TWB + 4 * C;
+    int16_t *__restrict__ plane = partial + (size_t)m * a.N * a.H * WC;
+    bool lut_ready = false;
+
+    for (long long tile = slot; tile < n_tiles; tile += ctas_per_mode) {
+        const int tx = (int)(tile % tiles_x);
+        const long long tr = tile / tiles_x;
+        const int ty = (int)(tr % tiles_y);
+        const int n = (int)(tr / tiles_y);
+        const int y0 = ty * S1_TH, X0 = tx * TWB;
+        const uint8_t *__restrict__ img = a.in + (size_t)n * a.H * WC;
+
+        __syncthreads();                       // previous tile fully consumed
+        fill_tile(s_in, P, S1_TH + 4, cols, img, a.H, C, WC, y0, X0);
+        __syncthreads();
+        if (!lut_ready) {                      // wait for the bulk copy (phase 0)
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.b32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(bar_addr), "r"(0u)
+                    : "memory");
+            }
+            lut_ready = true;
+        }
+        const int xb = X0 + lx;
+#pragma unroll 1
+        for (int ly = rp; ly < S1_TH; ly += S1_RW) {
+            const int y = y0 + ly;
+            const uint8_t *sp = s_in + (ly + 2) * P + lx + 2 * C;
+            int acc;
+            switch (mode) {
+            case 's': acc = smem_lut_sample<'s', CT>(sp, C, slut); break;
+            case 'd': acc = smem_lut_sample<'d', CT>(sp, C, slut); break;
+            default: acc = smem_lut_sample<'y', CT>(sp, C, slut); break;
+            }
+            if (y < a.H && xb < WC) plane[((size_t)n * a.H + y) * WC + xb] = (int16_t)acc;
+        }
+    }
+    if (!lut_ready) {                          // never leave with a bulk copy in flight
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.b32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar_addr), "r"(0u)
+                : "memory");
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1b: sum the per-mode planes + stage epilogue (sr/4_test_lut.py:281-286,300-306)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+combine_kernel(const int16_t *__restrict__ partial, uint8_t *__restrict__ out, size_t total,
+               int n_modes, int last)
+{
+    const uint32_t den = last ? 16u * n_modes : 64u * n_modes;
+    const int bias = last ? 0 : 127 * (int)den;
+    // 8 samples per thread when the planes allow 16-byte loads
+    const bool vec = (total % 8 == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+    const size_t total8 = vec ? total / 8 : 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
+         i += (size_t)gridDim.x * blockDim.x) {
+        int s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int m = 0; m < n_modes; ++m) {
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(partial + (size_t)m * total) + i);
+            const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                s[2 * k] += (int)(int16_t)(w[k] & 0xffff);
+                s[2 * k + 1] += w[k] >> 16;
+            }
+        }
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            lo |= rhe_div_clamp_u8(s[k] + bias, den) << (8 * k);
+            hi |= rhe_div_clamp_u8(s[4 + k] + bias, den) << (8 * k);
+        }
+        reinterpret_cast<uint2 *>(out)[i] = make_uint2(lo, hi);
+    }
+    if (total8 == 0) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += (size_t)gridDim.x * blockDim.x) {
+            int s = 0;
+            for (int m = 0; m < n_modes; ++m) s += partial[(size_t)m * total + i];
+            out[i] = (uint8_t)rhe_div_clamp_u8(s + bias, den);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1c: last stage, up = 2, cell-major LUT, quad-cooperative gathers
+// ---------------------------------------------------------------------------
+constexpr int Q2_TH = 16;
+constexpr int Q2_RW = 4;
+constexpr int Q2_THREADS = 96 * Q2_RW;
+constexpr int Q2_OP = 2 * TWB;          // output tile pitch in bytes
+
+// weights of this lane's four corners (c,d in {00,01,10,11}) packed as bytes.
+// w(S) = relu(min_{i in S} f_i - max_{i not in S} f_i), S = corner's tap set;
+// non-zero exactly on the five path vertices of the sorted-simplex walk.
+__device__ __forceinline__ uint32_t corner_weights4(uint32_t rq, bool la, bool lb)
+{
+    const int fa = (rq >> 12) & 15, fb = (rq >> 8) & 15, fc = (rq >> 4) & 15, fd = rq & 15;
+    const int ain = min(la ? fa : 16, lb ? fb : 16);
+    const int aout = max(la ? 0 : fa, lb ? 0 : fb);
+    const int mn = min(fc, fd), mx = max(fc, fd);
+    const int w00 = max(ain - max(aout, mx), 0);
+    const int w01 = max(min(ain, fd) - max(aout, fc), 0);
+    const int w10 = max(min(ain, fc) - max(aout, fd), 0);
+    const int w11 = max(min(ain, mn) - aout, 0);
+    return (uint32_t)w00 | ((uint32_t)w01 << 8) | ((uint32_t)w10 << 16) | ((uint32_t)w11 << 24);
+}
+
+template <char MODE, int CT>
+__device__ __forceinline__ void quad_mode(const uint8_t *__restrict__ sp, int C,
+                                          const uint8_t *__restrict__ cells, int ql, bool la, bool lb,
+                                          uint32_t (&acc)[4][4])
+{
+    constexpr int P = tile_pitch<CT>();
+    const int Cc = CT > 0 ? CT : C;
+    const uint32_t t0 = sp[0];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t t1 = sp[tap_off(MODE, r, 1, true) * P + tap_off(MODE, r, 1, false) * Cc];
+        const uint32_t t2 = sp[tap_off(MODE, r, 2, true) * P + tap_off(MODE, r, 2, false) * Cc];
+        const uint32_t t3 = sp[tap_off(MODE, r, 3, true) * P + tap_off(MODE, r, 3, false) * Cc];
+        // request word: cell id (m_a m_b m_c m_d nibbles) << 16 | fractions (f_a f_b f_c f_d nibbles)
+        const uint32_t cell = ((t0 >> 4) << 12) | ((t1 >> 4) << 8) | ((t2 >> 4) << 4) | (t3 >> 4);
+        const uint32_t fr = ((t0 & 15u) << 12) | ((t1 & 15u) << 8) | ((t2 & 15u) << 4) | (t3 & 15u);
+        const uint32_t req = (cell << 16) | fr;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const uint32_t rq = __shfl_sync(FULL, req, s, 4);
+            const uint4 d = __ldg(reinterpret_cast<const uint4 *>(cells + (size_t)(rq >> 16) * 64 + ql * 16));
+            const uint32_t wp = corner_weights4(rq, la, lb);
+            acc[s][subpixel_perm<2>(r, 0)] = __dp4a(d.x, wp, acc[s][subpixel_perm<2>(r, 0)]);
+            acc[s][subpixel_perm<2>(r, 1)] = __dp4a(d.y, wp, acc[s][subpixel_perm<2>(r, 1)]);
+            acc[s][subpixel_perm<2>(r, 2)] = __dp4a(d.z, wp, acc[s][subpixel_perm<2>(r, 2)]);
+            acc[s][subpixel_perm<2>(r, 3)] = __dp4a(d.w, wp, acc[s][subpixel_perm<2>(r, 3)]);
+        }
+    }
+}
+
+template <int CT>
+__global__ void __launch_bounds__(Q2_THREADS, 2)
+stage_last2_quad_kernel(const __grid_constant__ StageArgs a)
+{
+    constexpr int P = tile_pitch<CT>();
+    __shared__ __align__(16) uint8_t s_in[(Q2_TH + 4) * P];
+    __shared__ __align__(16) uint8_t s_out[2 * Q2_TH * Q2_OP];
+
+    const int C = CT > 0 ? CT : a.C;
+    const int WC = a.W * C;
+    const int tiles_x = (WC + TWB - 1) / TWB;
+    const int tiles_y = (a.H + Q2_TH - 1) / Q2_TH;
+    const long long n_tiles = (long long)a.N * tiles_y * tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lx = (warp % 3) * 32 + lane;
+    const int rp = warp / 3;
+    const int ql = lane & 3;
+    const bool la = (ql & 2) != 0, lb = (ql & 1) != 0;
+    const int ocol0 = lx + C * (lx / C);             // (2*(lx/C))*C + lx%C
+    const int cols = TWB + 4 * C;
+    const int oWC = 2 * WC;                          // output row pitch in bytes
+    const uint32_t bias_total = (uint32_t)a.n_modes * 4u * 2048u;   // 16*128 per interpolation
+    const uint32_t den = 16u * a.n_modes;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tx = (int)(tile % tiles_x);
+        const long long tr = tile / tiles_x;
+        const int ty = (int)(tr % tiles_y);
+        const int n = (int)(tr / tiles_y);
+        const int y0 = ty * Q2_TH, X0 = tx * TWB;
+        const uint8_t *__restrict__ img = a.in + (size_t)n * a.H * WC;
+
+        __syncthreads();                       // previous tile's s_in / s_out fully consumed
+        fill_tile(s_in, P, Q2_TH + 4, cols, img, a.H, C, WC, y0, X0);
+        __syncthreads();
+
+#pragma unroll 1
+        for (int ly = rp; ly < Q2_TH; ly += Q2_RW) {
+            const uint8_t *sp = s_in + (ly + 2) * P + lx + 2 * C;
+            uint32_t acc[4][4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[s][j] = 0u;
+            for (int m = 0; m < a.n_modes; ++m) {
+                const uint8_t *__restrict__ cells = a.lut_alt[m];
+                switch (a.modes[m]) {
+                case 's': quad_mode<'s', CT>(sp, C, cells, ql, la, lb, acc); break;
+                case 'd': quad_mode<'d', CT>(sp, C, cells, ql, la, lb, acc); break;
+                default: quad_mode<'y', CT>(sp, C, cells, ql, la, lb, acc); break;
+                }
+            }
+            // quad butterfly: lane ql ends with the complete sums of sample slot ql
+            uint32_t tot[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t keep01 = lb ? acc[1][j] : acc[0][j];
+                const uint32_t send01 = lb ? acc[0][j] : acc[1][j];
+                const uint32_t keep23 = lb ? acc[3][j] : acc[2][j];
+                const uint32_t send23 = lb ? acc[2][j] : acc[3][j];
+                const uint32_t k01 = keep01 + __shfl_xor_sync(FULL, send01, 1);
+                const uint32_t k23 = keep23 + __shfl_xor_sync(FULL, send23, 1);
+                const uint32_t keep = la ? k23 : k01;
+                const uint32_t send = la ? k01 : k23;
+                tot[j] = keep + __shfl_xor_sync(FULL, send, 2);
+            }
+            uint8_t *so = s_out + (2 * ly) * Q2_OP + ocol0;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const int S = (int)tot[u * 2 + v] - (int)bias_total;
+                    so[u * Q2_OP + v * C] = (uint8_t)rhe_div_clamp_u8(S, den);
+                }
+        }
+        __syncthreads();
+
+        // coalesced copy-out of the (2*TH) x (2*TWB) byte tile
+        uint8_t *__restrict__ outn = a.out + (size_t)n * (2 * a.H) * oWC;
+        const int oy0 = 2 * y0, oX0 = 2 * X0;
+        const int rows_valid = min(2 * Q2_TH, 2 * a.H - oy0);
+        const int cols_valid = min(Q2_OP, oWC - oX0);
+        const bool vec_ok = ((oWC & 15) == 0) && ((reinterpret_cast<uintptr_t>(outn) & 15) == 0) &&
+                            (cols_valid == Q2_OP);
+        if (vec_ok) {
+            constexpr int VPR = Q2_OP / 16;    // 12 vectors per row
+            for (int idx = threadIdx.x; idx < rows_valid * VPR; idx += blockDim.x) {
+                const int r = idx / VPR, c16 = idx - r * VPR;
+                const uint4 v = *reinterpret_cast<const uint4 *>(s_out + r * Q2_OP + c16 * 16);
+                *reinterpret_cast<uint4 *>(outn + (size_t)(oy0 + r) * oWC + oX0 + c16 * 16) = v;
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < rows_valid * Q2_OP; idx += blockDim.x) {
+                const int r = idx / Q2_OP, c = idx - r * Q2_OP;
+                if (c < cols_valid) outn[(size_t)(oy0 + r) * oWC + oX0 + c] = s_out[r * Q2_OP + c];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// LUT re-layouts
+// ---------------------------------------------------------------------------
+// up = 1: the "alt" table is the int8 LUT itself padded to LUT1_SMEM bytes.
+// up = 2: cell-major, 64 B per cell:  byte[cell*64 + l*16 + j*4 + cd] =
+//         LUT[(ma+la)*17^3 + (mb+lb)*17^2 + (mc+c)*17 + (md+d)][j] + 128,
+//         l = la*2+lb, cd = c*2+d, cell = ma<<12 | mb<<8 | mc<<4 | md.
+__global__ void build_cell_major2_kernel(const int8_t *__restrict__ lut, uint8_t *__restrict__ cells)
+{
+    const size_t total = (size_t)65536 * 64;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int cd = i & 3, j = (i >> 2) & 3, l = (i >> 4) & 3;
+        const int cell = (int)(i >> 6);
+        const int ma = cell >> 12, mb = (cell >> 8) & 15, mc = (cell >> 4) & 15, md = cell & 15;
+        const int v = (ma + (l >> 1)) * 4913 + (mb + (l & 1)) * 289 + (mc + (cd >> 1)) * 17 + (md + (cd & 1));
+        cells[i] = (uint8_t)((int)lut[(size_t)v * 4 + j] + 128);
+    }
+}
+
+size_t cell_major_bytes(int up)
+{
+    if (up == 1) return LUT1_SMEM;
+    if (up == 2) return (size_t)65536 * 64;
+    return 0;
+}
+
+int build_cell_major(const int8_t *d_lut, uint8_t *d_alt, int up, cudaStream_t stream)
+{
+    if (up == 1) {
+        MULUT_CUDA(cudaMemsetAsync(d_alt, 0, LUT1_SMEM, stream));
+        MULUT_CUDA(cudaMemcpyAsync(d_alt, d_lut, LUT1_ROWS, cudaMemcpyDeviceToDevice, stream));
+        return MULUT_OK;
+    }
+    if (up == 2) {
+        build_cell_major2_kernel<<<1024, 256, 0, stream>>>(d_lut, d_alt);
+        MULUT_CUDA(cudaGetLastError());
+        return MULUT_OK;
+    }
+    return MULUT_OK;
+}
+
+bool tiled_supported(int up, int interval, int n_modes)
+{
+    return interval == 4 && n_modes >= 1 && (up == 1 || up == 2);
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+template <typename K>
+static int set_smem(K kernel, size_t bytes)
+{
+    MULUT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return MULUT_OK;
+}
+
+template <int CT>
+static int launch_smem_stage(const StageArgs &a, int16_t *partial, cudaStream_t stream)
+{
+    constexpr int P = tile_pitch<CT>();
+    const size_t smem = LUT1_SMEM + (size_t)(S1_TH + 4) * P;
+    {
+        int rc = set_smem(stage_smem_kernel<CT>, smem);
+        if (rc) return rc;
+    }
+    int per_sm = 0;
+    MULUT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_smem_kernel<CT>, S1_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    int resident = per_sm * a.num_sms;
+    int ctas_per_mode = resident / a.n_modes;
+    if (ctas_per_mode < 1) ctas_per_mode = 1;
+    const int WC = a.W * a.C;
+    const long long n_tiles = (long long)a.N * ((a.H + S1_TH - 1) / S1_TH) * ((WC + TWB - 1) / TWB);
+    if (ctas_per_mode > n_tiles) ctas_per_mode = (int)n_tiles;
+    stage_smem_kernel<CT><<<ctas_per_mode * a.n_modes, S1_THREADS, smem, stream>>>(a, partial, ctas_per_mode);
+    MULUT_CUDA(cudaGetLastError());
+    return MULUT_OK;
+}
+
+template <int CT>
+static int launch_quad_stage(const StageArgs &a, cudaStream_t stream)
+{
+    int per_sm = 0;
+    MULUT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_last2_quad_kernel<CT>, Q2_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    const int WC = a.W * a.C;
+    const long long n_tiles = (long long)a.N * ((a.H + Q2_TH - 1) / Q2_TH) * ((WC + TWB - 1) / TWB);
+    long long grid = (long long)per_sm * a.num_sms;
+    if (grid > n_tiles) grid = n_tiles;
+    stage_last2_quad_kernel<CT><<<(unsigned)grid, Q2_THREADS, 0, stream>>>(a);
+    MULUT_CUDA(cudaGetLastError());
+    return MULUT_OK;
+}
+
+// partial: workspace of n_modes * N*H*W*C int16 (only used for up == 1)
+int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStream_t stream, int *launches)
+{
+    const size_t total = (size_t)a.N * a.H * a.W * a.C;
+    if (total == 0) return MULUT_OK;
+    if (!tiled_supported(up, a.interval, a.n_modes)) return 1;
+    if (a.C != 1 && a.C != 2 && a.C != 3 && a.C != 4) return 1;
+    if (up == 1) {
+        int rc = a.C == 3 ? launch_smem_stage<3>(a, partial, stream)
+               : a.C == 1 ? launch_smem_stage<1>(a, partial, stream)
+                          : launch_smem_stage<0>(a, partial, stream);
+        if (rc) return rc;
+        size_t blocks = (total / 8 + 255) / 256 + 1;
+        const size_t cap = (size_t)a.num_sms * 16;
+        if (blocks > cap) blocks = cap;
+        combine_kernel<<<(unsigned)blocks, 256, 0, stream>>>(partial, a.out, total, a.n_modes, a.last);
+        MULUT_CUDA(cudaGetLastError());
+        *launches += 2;
+        return MULUT_OK;
+    }
+    if (!a.last) return 1;
+    int rc = a.C == 3 ? launch_quad_stage<3>(a, stream)
+           : a.C == 1 ? launch_quad_stage<1>(a, stream)
+                      : launch_quad_stage<0>(a, stream);
+    if (rc) return rc;
+    *launches += 1;
+    return MULUT_OK;
+}
+
+}  // namespace mulut

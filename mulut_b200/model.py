@@ -1,0 +1,134 @@
+"""LUT-aware fine-tuning model: drop-in for the reference's `model.MuLUT`
+(sr/model.py:39-312) with `InterpTorchBatch` backed by the sm_100a kernels.
+
+Same constructor, parameter names (`weight_s{stage}_{mode}`), file-name rule
+(`LUT_x{r}_{interval}bit_int8_s{stage}_{mode}.npy`, model.py:53-54), forward
+semantics (per-rotation BPDA rounding, model.py:305-309) and `InterpTorchBatch`
+signature.  Autograd is supplied by a torch.autograd.Function that calls
+mulut_interp_fwd_f32 / mulut_interp_bwd_f32 through the C ABI; there is no
+ATen fallback (CPU tensors raise).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+mode_pad_dict = {"s": 1, "d": 2, "y": 2, "e": 3, "h": 3, "o": 3}    # model.py:12
+
+
+class _InterpFunction(torch.autograd.Function):
+    """K2/K3: forward and backward of MuLUT.InterpTorchBatch (model.py:69-287)."""
+
+    @staticmethod
+    def forward(ctx, weight, img_in, upscale, mode, bd, interval):
+        if not (weight.is_cuda and img_in.is_cuda):
+            raise RuntimeError("mulut_b200 InterpTorchBatch needs CUDA tensors (no CPU fallback)")
+        w = weight.detach().contiguous().float()
+        x = img_in.detach().contiguous().float()
+        B, C, Hp, Wp = x.shape
+        h, wd = Hp - bd, Wp - bd
+        out = torch.empty((B, C, h * upscale, wd * upscale), dtype=torch.float32, device=x.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().mulut_interp_fwd_f32(w.data_ptr(), w.shape[0], upscale, mode.encode(), x.data_ptr(),
+                                                       B, C, h, wd, bd, interval, out.data_ptr(), stream))
+        ctx.save_for_backward(w, x)
+        ctx.cfg = (upscale, mode, bd, interval, B, C, h, wd)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        w, x = ctx.saved_tensors
+        upscale, mode, bd, interval, B, C, h, wd = ctx.cfg
+        g = grad_out.contiguous().float()
+        gw = torch.zeros_like(w) if ctx.needs_input_grad[0] else None
+        gx = torch.zeros_like(x) if ctx.needs_input_grad[1] else None
+        stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().mulut_interp_bwd_f32(
+                w.data_ptr(), w.shape[0], upscale, mode.encode(), x.data_ptr(), B, C, h, wd, bd, interval,
+                g.data_ptr(), gw.data_ptr() if gw is not None else None,
+                gx.data_ptr() if gx is not None else None, stream))
+        return gw, gx, None, None, None, None
+
+
+def interp_torch_batch(weight, upscale, mode, img_in, bd, interval=4):
+    if mode not in ("s", "d", "y"):
+        raise ValueError("Mode {} not implemented.".format(mode))      # model.py:119-121
+    return _InterpFunction.apply(weight, img_in, int(upscale), mode, int(bd), int(interval))
+
+
+class MuLUT(nn.Module):
+    """PyTorch version of MuLUT for LUT-aware fine-tuning (kernel-backed)."""
+
+    def __init__(self, lut_folder, stages, modes, upscale=4, interval=4, luts=None):
+        super().__init__()
+        self.interval = interval
+        self.upscale = upscale
+        self.modes = modes
+        self.stages = stages
+        for s in range(stages):
+            stage = s + 1
+            scale = upscale if stage == stages else 1
+            for mode in modes:
+                key = "s{}_{}".format(stage, mode)
+                if luts is not None:
+                    arr = np.asarray(luts[key])
+                else:
+                    arr = np.load(os.path.join(
+                        lut_folder, "LUT_x{}_{}bit_int8_s{}_{}.npy".format(upscale, interval, stage, mode)))
+                lut_arr = arr.reshape(-1, scale * scale).astype(np.float32) / 127.0
+                self.register_parameter(name="weight_" + key, param=nn.Parameter(torch.Tensor(lut_arr)))
+
+    @staticmethod
+    def round_func(input):
+        """BPDA: round forward, identity backward (model.py:59-67)."""
+        return input + (torch.round(input) - input).detach()
+
+    def InterpTorchBatch(self, weight, upscale, mode, img_in, bd):
+        return interp_torch_batch(weight, upscale, mode, img_in, bd, self.interval)
+
+    def forward(self, x):
+        x = x * 255.0
+        modes, stages = self.modes, self.stages
+        for s in range(stages):
+            pred = 0
+            stage = s + 1
+            if stage == stages:
+                avg_factor, bias = len(modes), 0
+                scale = self.upscale
+            else:
+                avg_factor, bias = len(modes) * 4, 127
+                scale = 1
+            for mode in modes:
+                pad = mode_pad_dict[mode]
+                weight = getattr(self, "weight_s{}_{}".format(stage, mode))
+                for r in [0, 1, 2, 3]:
+                    xin = F.pad(torch.rot90(x, r, [2, 3]), (0, pad, 0, pad), mode="replicate")
+                    pred = pred + torch.rot90(self.InterpTorchBatch(weight, scale, mode, xin, pad), (4 - r) % 4, [2, 3])
+                    pred = self.round_func(pred)
+            x = self.round_func(torch.clamp((pred / avg_factor) + bias, 0, 255))
+        return x / 255.0
+
+    # -- the on-disk format's writer (3_finetune_lut.py:162-169) -------------------
+    def export_luts(self, exp_dir=None):
+        """round(clip(w,-1,1)*127).int8 per table; optionally saved as
+        LUT_ft_x{r}_{interval}bit_int8_s{stage}_{mode}.npy."""
+        out = {}
+        for s in range(self.stages):
+            for mode in self.modes:
+                key = "s{}_{}".format(s + 1, mode)
+                w = getattr(self, "weight_" + key).detach().cpu().numpy()
+                lut = np.round(np.clip(w, -1, 1) * 127).astype(np.int8)
+                out[key] = lut
+                if exp_dir is not None:
+                    np.save(os.path.join(exp_dir, "LUT_ft_x{}_{}bit_int8_s{}_{}.npy".format(
+                        self.upscale, self.interval, s + 1, mode)), lut)
+        return out
