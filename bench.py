@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the MuLUT LUT-retrieval hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): output Mpix/s of sr_x2sdy 2-stage LUT inference,
+1920x1080 RGB frames -> 3840x2160 (scale 2, modes s,d,y, interval 4), seeded
+random int8 LUTs (no x2 LUT is shipped by the reference), synthetic uniform
+uint8 frames.  One "step" = one pass of the path over --frames frames per GPU.
+Frames are sharded across ranks with no collective (weak scaling).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, C, SCALE, STAGES, MODES, INTERVAL = 1080, 1920, 3, 2, 2, "sdy", 4
+WORKLOAD = "cfg2: sr_x2sdy 2-stage, 1920x1080x3 uint8 -> 3840x2160x3, scale 2, random int8 LUTs (seed 1)"
+# algorithmic bytes per input sample (SURVEY.md 8d / DESIGN.md): 12*5 vertex rows of 1 B in
+# stage 1, 12*5 rows of r^2 = 4 B in stage 2; HBM: 1 B read + r^2 written.
+GATHER_B_STAGE1, GATHER_B_STAGE2, HBM_B = 60, 240, 5
+
+
+def make_luts(seed=1):
+    rng = np.random.default_rng(seed)
+    luts = {}
+    for s in range(STAGES):
+        cols = SCALE * SCALE if s + 1 == STAGES else 1
+        for m in MODES:
+            luts["s{}_{}".format(s + 1, m)] = rng.integers(-127, 128, (83521, cols), dtype=np.int8)
+    return luts
+
+
+def make_frames(n, seed):
+    return np.random.default_rng(seed).integers(0, 256, (n, H, W, C), dtype=np.uint8)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def gather_peak(device):
+    """Measured denominators of the gather roofline (GB/s of 32-byte sectors that
+    L2 can deliver to the SMs under random cell fetches), live, ~0.2 s."""
+    from mulut_b200 import _lib
+    L = _lib.lib()
+    out = (ctypes.c_double * 3)()
+    res = {}
+    for name, table, bps, tpb in [("quad_cell64", 12 << 20, 4, 512), ("ldg_u32", 1 << 20, 4, 512),
+                                  ("lds_u8", 83584, 2, 512)]:
+        rc = L.mulut_gather_bench(device, _lib.GB_VARIANTS[name], table, 256, bps, tpb, 3, out)
+        if rc == 0:
+            res[name] = {"gathers_per_s": out[0], "useful_GBps": out[1] / 1e9}
+    return res
+
+
+def cpu_port_throughput(min_seconds, max_frames, threads=0):
+    """The C oracle (oracle/mulut_oracle.c, kind 'port') on this host's cores."""
+    from oracle import c_oracle as CO
+    luts = make_luts()
+    frame = make_frames(1, 1234)
+    CO.sr_u8(frame[:, :64], luts, STAGES, MODES, SCALE, INTERVAL, threads)      # warm (build + page in)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        CO.sr_u8(frame, luts, STAGES, MODES, SCALE, INTERVAL, threads)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds or n >= max_frames:
+            break
+    cores = threads if threads > 0 else CO.max_threads()
+    return n * H * W * SCALE * SCALE / dt / 1e6, cores, n, dt
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU path.  The reference is pure Python
+    and /root/reference does not exist on the GPU box, so this is the C port of
+    the same algorithm (oracle/, pinned bit-exact to the reference's golden
+    outputs), on all host threads.  Each step = one 1080p frame."""
+    if rank != 0:
+        return
+    from oracle import c_oracle as CO
+    luts = make_luts()
+    frame = make_frames(1, 0)
+    cores = CO.max_threads()
+    for _ in range(args.warmup):
+        CO.sr_u8(frame, luts, STAGES, MODES, SCALE, INTERVAL, 0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        CO.sr_u8(frame, luts, STAGES, MODES, SCALE, INTERVAL, 0)
+    dt = time.perf_counter() - t0
+    val = args.steps * H * W * SCALE * SCALE / dt / 1e6
+    sample = "{} steps x 1 frame 1920x1080 (C port of the reference algorithm, pthreads over rows)".format(args.steps)
+    line = {
+        "impl": "reference", "metric": "output Mpix/s", "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": 1, "device": "cpu"},
+        "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", type=str, default="mulut_b200", choices=["mulut_b200", "reference"])
+    ap.add_argument("--frames", type=int, default=16, help="1080p frames per GPU per step")
+    ap.add_argument("--kernel", type=str, default="auto", choices=["auto", "generic", "tiled"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mulut_b200 import _lib
+    from mulut_b200.infer import LutEngine, pinned_empty
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+
+    kernel = {"auto": _lib.KERNEL_AUTO, "generic": _lib.KERNEL_GENERIC, "tiled": _lib.KERNEL_TILED}[args.kernel]
+    luts = make_luts()
+    eng = LutEngine(luts, STAGES, MODES, SCALE, INTERVAL, device=local, kernel=kernel)
+    F = args.frames
+    host_in = pinned_empty((F, H, W, C))
+    host_in[...] = make_frames(F, seed=1000 + rank)
+    host_out = pinned_empty((F, H * SCALE, W * SCALE, C))
+    d_in = torch.from_numpy(np.ascontiguousarray(host_in)).cuda()
+    d_out = torch.empty((F, H * SCALE, W * SCALE, C), dtype=torch.uint8, device="cuda")
+    eng.reserve(F, H, W, C)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident leg (value) ----------------
+    for _ in range(args.warmup):
+        eng.infer_device(d_in, d_out)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.profile(True)
+    launches0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        eng.infer_device(d_in, d_out)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count - launches0
+    prof = eng.profile_read()
+    eng.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    out_pix_per_step = world * F * H * W * SCALE * SCALE
+    value = out_pix_per_step * args.steps / (ms_max * 1e-3) / 1e6
+
+    # ---------------- end-to-end leg: host buffers through the C ABI ----------------
+    for _ in range(2):
+        eng.infer_host(host_in, host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.infer_host(host_in, host_out)       # synchronous: H2D + kernels + D2H inside
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = out_pix_per_step * args.steps / float(t.item()) / 1e6
+    sanity = int(host_out[0, :8, :8].sum())    # device->host read of the step's result
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel ----------------
+    samples_per_step = F * H * W * C
+    hbm_peak, peak_src = measured_peaks()
+    dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, (0.0, 0))
+    dom_name, (dom_ms, dom_n) = dom
+    gather_b = {"last_tiled": GATHER_B_STAGE2, "generic_last": GATHER_B_STAGE2, "smem_stage": GATHER_B_STAGE1,
+                "generic_stage": GATHER_B_STAGE1, "combine": 0}.get(dom_name, 0)
+    hbm_b = {"last_tiled": 1 + SCALE * SCALE, "generic_last": 1 + SCALE * SCALE, "smem_stage": 1 + 2 * len(MODES),
+             "generic_stage": 2, "combine": 2 * len(MODES) + 1}.get(dom_name, HBM_B)
+    per_launch_s = dom_ms * 1e-3 / max(dom_n, 1)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom_name)
+        except Exception:
+            traffic = None
+    ach_hbm = samples_per_step * hbm_b / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": ach_hbm, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach_hbm / hbm_peak, "traffic": traffic, "peak_source": peak_src + " (of measured)",
+                "alg_bytes_per_sample": hbm_b, "launch_ms": per_launch_s * 1e3,
+                "share_of_step": dom_ms / ms if ms > 0 else None,
+                "note": "path is cache-gather bound, not HBM bound: see gather_roofline"}
+    gp = gather_peak(local)
+    ach_gather = samples_per_step * gather_b / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+    # denominator: cells/s of the best L2 cell-fetch shape x the 20 B (5 vertices x 4 B) an interpolation needs
+    cell_rate = gp.get("quad_cell64", {}).get("gathers_per_s", 0.0)
+    gather_roofline = {
+        "bound": "l2_gather", "kernel": dom_name, "achieved": ach_gather, "unit": "GB/s",
+        "alg_gather_bytes_per_sample": gather_b,
+        "peak": cell_rate * 20 / 1e9 if cell_rate else None,
+        "peak_def": "measured random 64-B cell fetches/s from an L2-resident 12 MB table (4 lanes x LDG.128) x 20 "
+                    "algorithmic bytes (5 vertices x 4 B) per fetch",
+        "frac": (ach_gather / (cell_rate * 20 / 1e9)) if cell_rate else None,
+        "whole_step_achieved": samples_per_step * (GATHER_B_STAGE1 + GATHER_B_STAGE2) * args.steps / (ms * 1e-3) / 1e9,
+        "microbench": gp,
+    }
+    kernels = {k: {"ms_total": v[0], "launches": v[1], "ms_per_launch": v[0] / v[1]} for k, v in prof.items()}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v, cores, n, dt_cpu = cpu_port_throughput(args.cpu_seconds, 64)
+        cpu = {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port",
+               "sample": "{} frame(s) 1920x1080 in {:.1f} s, C port of the reference algorithm (oracle/mulut_oracle.c), "
+                         "pthreads over rows".format(n, dt_cpu)}
+
+    line = {
+        "metric": "output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "kernel": args.kernel,
+                   "l2": "per-step working set per GPU = {:.0f} MB in + {:.0f} MB out (> 126 MB L2), no flush".format(
+                       F * H * W * C / 1e6, F * H * W * C * SCALE * SCALE / 1e6),
+                   "parallelism": "frames sharded over {} GPU(s), no collective".format(world)},
+        "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": F * H * W * C,
+                "d2h_bytes_per_step": F * H * W * C * SCALE * SCALE, "api": "LutEngine.infer_host -> mulut_sr_infer_u8_host",
+                "host_memory": "pinned", "check": sanity},
+        "gpu_launches": int(launches) * world,
+        "clocks": clocks,
+        "roofline": roofline,
+        "gather_roofline": gather_roofline,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

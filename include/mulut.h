@@ -84,6 +84,21 @@ int mulut_sr_infer_u8_host(mulut_handle_t handle, const uint8_t *h_in, uint8_t *
 long long mulut_launch_count(mulut_handle_t handle);
 
 /*
+ * Per-kernel device timing for the roofline report (bench.py): while enabled,
+ * every kernel launch of this handle is bracketed by CUDA events on the stream
+ * it is launched on.  mulut_profile_read synchronises those events and returns
+ * the summed duration and launch count of one kernel kind.
+ */
+#define MULUT_PROF_GENERIC_STAGE  0   /* stage_generic_kernel, non-last stage */
+#define MULUT_PROF_GENERIC_LAST   1   /* stage_generic_kernel, last stage     */
+#define MULUT_PROF_SMEM_STAGE     2   /* stage_smem_kernel (K1a)              */
+#define MULUT_PROF_COMBINE        3   /* combine_kernel (K1b)                 */
+#define MULUT_PROF_LAST_TILED     4   /* tiled last-stage kernel (K1c)        */
+#define MULUT_PROF_KINDS          5
+int mulut_profile_enable(mulut_handle_t handle, int on);
+int mulut_profile_read(mulut_handle_t handle, int kind, double *total_ms, long long *launches);
+
+/*
  * Signature-compatible single pass: FourSimplexInterpFaster(weight, img_in, h, w,
  * interval, rot, upscale, mode), sr/4_test_lut.py:14-237.
  *   d_weight  float32 (n_rows, upscale^2)  (int8 values stored as float32, :333)

@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libmulut_b200.so")
 OK, E_BAD_MODE, E_BAD_ARG, E_CUDA, E_NOMEM, E_LUT_SMALL = 0, -1, -2, -3, -4, -5
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED = -1, 0, 1
 
+PROF_KINDS = {"generic_stage": 0, "generic_last": 1, "smem_stage": 2, "combine": 3, "last_tiled": 4}
+
 GB_VARIANTS = {
     "ldg_u8": 0, "ldg_u32": 1, "ldg_u128": 2, "quad_cell64": 3, "lds_u8": 4,
     "pair_cell64": 5, "oct_cell128": 6, "cpasync_cell64": 7, "lds_u32": 8,
@@ -34,6 +36,8 @@ SYMBOLS = {
     "mulut_sr_infer_u8_host": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
                                           _c.c_int]),
     "mulut_launch_count": (_c.c_longlong, [_c.c_void_p]),
+    "mulut_profile_enable": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "mulut_profile_read": (_c.c_int, [_c.c_void_p, _c.c_int, _c.POINTER(_c.c_double), _c.POINTER(_c.c_longlong)]),
     "mulut_interp_pass_f64": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                          _c.c_int, _c.c_int, _c.c_char, _c.c_void_p, _c.c_void_p]),
     "mulut_interp_fwd_f32": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_char, _c.c_void_p, _c.c_int, _c.c_int,

@@ -52,6 +52,7 @@ struct mulut_handle_s {
     uint8_t *lane_in[HOST_LANES] = {}, *lane_out[HOST_LANES] = {};
     size_t lane_in_bytes = 0, lane_out_bytes = 0;
     long long launches = 0;
+    Prof prof;
 };
 
 static int ws_reserve(Workspace &w, int stages, int n_modes, size_t frame_samples, bool want_partial)
@@ -118,12 +119,14 @@ static int run_stages(mulut_handle_s *h, Workspace &w, const uint8_t *d_in, uint
         int done = 1;
         if (uses_tiled(h, up, C)) {
             int launches = 0;
-            done = launch_stage_tiled_ws(a, up, w.partial, stream, &launches);
+            done = launch_stage_tiled_ws(a, up, w.partial, stream, &launches, &h->prof);
             if (done < 0) return done;
             h->launches += launches;
         }
         if (done == 1) {
+            h->prof.begin(last ? MULUT_PROF_GENERIC_LAST : MULUT_PROF_GENERIC_STAGE, stream);
             rc = launch_stage_generic(a, up, stream);
+            h->prof.end(stream);
             if (rc) return rc;
             h->launches += 1;
         }
@@ -255,6 +258,7 @@ int mulut_destroy(mulut_handle_t h)
         cudaFree(h->lane_out[i]);
     }
     for (auto &w : h->ws) ws_free(w);
+    for (int i = 0; i < h->prof.n_events; ++i) { cudaEventDestroy(h->prof.recs[i].e0); cudaEventDestroy(h->prof.recs[i].e1); }
     cudaFree(h->d_luts);
     delete h;
     return MULUT_OK;
@@ -271,6 +275,34 @@ int mulut_set_kernel(mulut_handle_t h, int kernel)
 }
 
 long long mulut_launch_count(mulut_handle_t h) { return h ? h->launches : 0; }
+
+int mulut_profile_enable(mulut_handle_t h, int on)
+{
+    if (!h) { set_error("null handle"); return MULUT_E_BAD_ARG; }
+    h->prof.n = 0;
+    h->prof.open = false;
+    h->prof.on = on != 0;
+    return MULUT_OK;
+}
+
+int mulut_profile_read(mulut_handle_t h, int kind, double *total_ms, long long *launches)
+{
+    if (!h || !total_ms || !launches || kind < 0 || kind >= MULUT_PROF_KINDS) {
+        set_error("mulut_profile_read: bad argument");
+        return MULUT_E_BAD_ARG;
+    }
+    *total_ms = 0.0;
+    *launches = 0;
+    for (int i = 0; i < h->prof.n; ++i) {
+        if (h->prof.recs[i].kind != kind) continue;
+        MULUT_CUDA(cudaEventSynchronize(h->prof.recs[i].e1));
+        float ms = 0.f;
+        MULUT_CUDA(cudaEventElapsedTime(&ms, h->prof.recs[i].e0, h->prof.recs[i].e1));
+        *total_ms += ms;
+        *launches += 1;
+    }
+    return MULUT_OK;
+}
 
 static int check_shape(mulut_handle_t h, const void *in, const void *out, int N, int H, int W, int C)
 {

@@ -19,12 +19,40 @@ struct StageArgs {
     TapTable taps;
 };
 
+// Optional per-launch event bracketing (mulut_profile_*).
+struct Prof {
+    bool on = false;
+    struct Rec { int kind; cudaEvent_t e0, e1; };
+    Rec recs[4096];
+    int n = 0, n_events = 0;           // records in use / records whose events exist
+    void begin(int kind, cudaStream_t st)
+    {
+        if (!on || n >= 4096) return;
+        if (n >= n_events) {
+            if (cudaEventCreate(&recs[n].e0) != cudaSuccess || cudaEventCreate(&recs[n].e1) != cudaSuccess) { on = false; return; }
+            n_events = n + 1;
+        }
+        recs[n].kind = kind;
+        cudaEventRecord(recs[n].e0, st);
+        open = true;
+    }
+    void end(cudaStream_t st)
+    {
+        if (!open) return;
+        cudaEventRecord(recs[n].e1, st);
+        ++n;
+        open = false;
+    }
+    bool open = false;
+};
+
 int launch_stage_generic(const StageArgs &a, int up, cudaStream_t stream);
 
 // Tiled sm_100a kernels (interval 4 only).  Return MULUT_OK, an error, or
 // +1 when the configuration is not covered (caller falls back to generic).
 // partial: workspace of n_modes * N*H*W*C int16 (used when up == 1).
-int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStream_t stream, int *launches);
+int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStream_t stream, int *launches,
+                          Prof *prof);
 bool tiled_supported(int up, int interval, int n_modes);
 
 // Device-side LUT re-layouts (run once at mulut_create).

@@ -484,29 +484,36 @@ static int launch_quad_stage(const StageArgs &a, cudaStream_t stream)
 }
 
 // partial: workspace of n_modes * N*H*W*C int16 (only used for up == 1)
-int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStream_t stream, int *launches)
+int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStream_t stream, int *launches,
+                          Prof *prof)
 {
     const size_t total = (size_t)a.N * a.H * a.W * a.C;
     if (total == 0) return MULUT_OK;
     if (!tiled_supported(up, a.interval, a.n_modes)) return 1;
     if (a.C != 1 && a.C != 2 && a.C != 3 && a.C != 4) return 1;
     if (up == 1) {
+        prof->begin(MULUT_PROF_SMEM_STAGE, stream);
         int rc = a.C == 3 ? launch_smem_stage<3>(a, partial, stream)
                : a.C == 1 ? launch_smem_stage<1>(a, partial, stream)
                           : launch_smem_stage<0>(a, partial, stream);
+        prof->end(stream);
         if (rc) return rc;
         size_t blocks = (total / 8 + 255) / 256 + 1;
         const size_t cap = (size_t)a.num_sms * 16;
         if (blocks > cap) blocks = cap;
+        prof->begin(MULUT_PROF_COMBINE, stream);
         combine_kernel<<<(unsigned)blocks, 256, 0, stream>>>(partial, a.out, total, a.n_modes, a.last);
+        prof->end(stream);
         MULUT_CUDA(cudaGetLastError());
         *launches += 2;
         return MULUT_OK;
     }
     if (!a.last) return 1;
+    prof->begin(MULUT_PROF_LAST_TILED, stream);
     int rc = a.C == 3 ? launch_quad_stage<3>(a, stream)
            : a.C == 1 ? launch_quad_stage<1>(a, stream)
                       : launch_quad_stage<0>(a, stream);
+    prof->end(stream);
     if (rc) return rc;
     *launches += 1;
     return MULUT_OK;

@@ -115,6 +115,20 @@ class LutEngine:
     def launch_count(self) -> int:
         return int(_lib.lib().mulut_launch_count(self._h))
 
+    def profile(self, on: bool) -> None:
+        """Bracket every kernel launch with CUDA events (bench.py's roofline leg)."""
+        _lib.check(_lib.lib().mulut_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self) -> dict:
+        """{kernel kind: (total_ms, launches)} since profile(True); synchronises."""
+        out = {}
+        for name, kind in _lib.PROF_KINDS.items():
+            ms, n = ctypes.c_double(), ctypes.c_longlong()
+            _lib.check(_lib.lib().mulut_profile_read(self._h, kind, ctypes.byref(ms), ctypes.byref(n)))
+            if n.value:
+                out[name] = (ms.value, n.value)
+        return out
+
     # -- hot path -------------------------------------------------------------
     def infer_device(self, frames, out=None):
         """frames: torch.uint8 CUDA tensor (N,H,W,C) or (H,W,C), contiguous.

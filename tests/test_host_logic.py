@@ -1,0 +1,192 @@
+"""CPU-side tests: the C ABI library loads and exports every symbol the header
+declares, file-name rules, options, sharding, the flat gradient bucket and the
+multi-process (gloo, world_size 2) plumbing."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    txt = open(os.path.join(ROOT, "include", "mulut.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mulut_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from mulut_b200 import _lib
+    names = _header_functions()
+    assert len(names) >= 14
+    assert sorted(_lib.SYMBOLS) == names            # binding table == header
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), n
+    L = _lib.lib()
+    assert L.mulut_version() >= 100
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_header_cites_reference_for_each_entry_point():
+    txt = open(os.path.join(ROOT, "include", "mulut.h")).read()
+    for cite in ("sr/4_test_lut.py:279-306", "sr/4_test_lut.py:14-237", "sr/model.py:69-287",
+                 "sr/4_test_lut.py:323-333"):
+        assert cite in txt, cite
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_product_fails_loudly_without_gpu(shipped_luts):
+    from mulut_b200 import _lib
+    from mulut_b200.infer import LutEngine
+    with pytest.raises(_lib.MulutError, match="CUDA error"):
+        LutEngine(shipped_luts, 2, "sdy", 4)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mulut_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# oracle-free", ""), os.path.join(dp, f)
+
+
+def test_lut_naming_rules(gold_dir):
+    from mulut_b200.infer import load_luts, lut_path
+    # test path: 8 - interval (4_test_lut.py:331-332)
+    assert os.path.basename(lut_path("e", "LUT_ft", 4, 4, 2, "y")) == "LUT_ft_x4_4bit_int8_s2_y.npy"
+    assert os.path.basename(lut_path("e", "LUT_ft", 2, 5, 1, "s")) == "LUT_ft_x2_3bit_int8_s1_s.npy"
+    luts = load_luts(os.path.join(gold_dir, "luts_x4"), 2, "sdy", 4, 4, "LUT_ft")
+    assert sorted(luts) == ["s1_d", "s1_s", "s1_y", "s2_d", "s2_s", "s2_y"]
+    assert luts["s1_s"].shape == (83521, 1) and luts["s2_d"].shape == (83521, 16) and luts["s2_d"].dtype == np.int8
+    with pytest.raises(FileNotFoundError):
+        load_luts(os.path.join(gold_dir, "luts_x4"), 2, "sdy", 2, 4, "LUT_ft")
+
+
+def test_options_match_reference_flags():
+    from mulut_b200.options import TestOptions, TrainOptions
+    o = TestOptions().parse(["--stages", "2", "--modes", "sdy", "-e", "../models/sr_x2sdy"])
+    assert (o.stages, o.modes, o.expDir, o.scale, o.interval, o.lutName) == (2, "sdy", "../models/sr_x2sdy", 4, 4, "LUT_ft")
+    assert (o.testDir, o.resultRoot, o.loadIter, o.isTrain) == ("../data/SRBenchmark", "../results", 200000, False)
+    o = TestOptions().parse(["-r", "2", "--interval", "5", "-i", "7"])
+    assert (o.scale, o.interval, o.loadIter) == (2, 5, 7) and o.expDir.startswith("../models/debug/expr_")
+    t = TrainOptions().parse(["-e", "x", "--batchSize", "256", "-g", "8"])
+    assert (t.batchSize, t.cropSize, t.totalIter, t.lr0, t.lr1, t.gpuNum, t.isTrain) == (256, 48, 200000, 1e-3, 1e-4, 8, True)
+
+
+def test_shard_range_partitions_exactly():
+    from mulut_b200.dist import shard_range, shard_rows_with_halo
+    for n in (0, 1, 7, 8, 64, 1001):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+    b, e, lb, le = shard_rows_with_halo(1080, 1, 4, 4)
+    assert (b, e, lb, le) == (270, 540, 266, 544)
+    assert shard_rows_with_halo(1080, 0, 4, 4)[2] == 0 and shard_rows_with_halo(1080, 3, 4, 4)[3] == 1080
+    with pytest.raises(ValueError):
+        shard_range(4, 4, 4)
+
+
+def test_mulut_module_parameters_and_export(tmp_path, shipped_luts):
+    from mulut_b200.model import MuLUT
+    net = MuLUT(None, 2, ["s", "d", "y"], upscale=4, interval=4, luts=shipped_luts)
+    names = [n for n, _ in net.named_parameters()]
+    assert names == ["weight_s1_s", "weight_s1_d", "weight_s1_y", "weight_s2_s", "weight_s2_d", "weight_s2_y"]
+    assert sum(p.numel() for p in net.parameters()) == 4259571      # 17.04 MB fp32
+    out = net.export_luts(str(tmp_path))
+    for k, v in shipped_luts.items():
+        assert (out[k] == v).all()                                   # int8/127 -> round(.*127) round trip
+        assert (np.load(tmp_path / "LUT_ft_x4_4bit_int8_{}.npy".format(k)) == v).all()
+    # loading by the finetune naming rule (model.py:53-54: `interval`, not 8-interval)
+    for k, v in shipped_luts.items():
+        np.save(tmp_path / "LUT_x4_4bit_int8_{}.npy".format(k), v)
+    net2 = MuLUT(str(tmp_path), 2, ["s", "d", "y"], upscale=4, interval=4)
+    assert torch.equal(net2.weight_s2_y, net.weight_s2_y)
+    x = torch.tensor([0.4, 0.5, 1.5, 2.5, -0.5])
+    assert torch.equal(MuLUT.round_func(x), torch.round(x))
+
+
+def test_lr_schedule_matches_reference_formula():
+    from mulut_b200.cli.finetune_lut import lr_lambda
+    f = lr_lambda(2000, 1e-3, 1e-4)
+    assert abs(f(0) - 1.0) < 1e-12 and abs(f(2000) - 0.1) < 1e-12 and abs(f(1000) - 0.55) < 1e-12
+    g = lr_lambda(100, 1e-3, -1)
+    assert abs(g(100) - 0.2) < 1e-12
+
+
+def test_flat_grad_bucket_single_process():
+    from mulut_b200.dist import FlatGradBucket
+    ps = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7))]
+    b = FlatGradBucket(ps)
+    (ps[0].sum() * 2 + (ps[1] * 3).sum()).backward()
+    assert b.flat.numel() == 22
+    assert torch.equal(b.flat[:15], torch.full((15,), 2.0)) and torch.equal(b.flat[15:], torch.full((7,), 3.0))
+    b.zero_()
+    assert float(b.flat.abs().sum()) == 0 and ps[0].grad.data_ptr() == b.flat.data_ptr()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from mulut_b200.dist import FlatGradBucket, shard_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    w = [torch.nn.Parameter(torch.randn(11, 4)), torch.nn.Parameter(torch.randn(6))]
+    data = torch.arange(40, dtype=torch.float32).reshape(10, 4)
+    b, e = shard_range(10, rank, world)
+    bucket = FlatGradBucket(w)
+    x = data[b:e]
+    # per-rank MEAN loss over an equal share, like F.mse_loss on the rank's batch
+    loss = ((x @ w[0][:4] ).pow(2).mean() + w[1].sum() * x.mean())
+    loss.backward()
+    bucket.all_reduce_mean()
+    q.put((rank, bucket.flat.clone().numpy(), (b, e)))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_allreduce_equals_full_batch():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    [p.join(60) for p in procs]
+    assert res[0][2] == (0, 5) and res[1][2] == (5, 10)
+    assert np.allclose(res[0][1], res[1][1])
+    # single-process reference on the whole batch (equal shares => mean of means == global mean)
+    torch.manual_seed(0)
+    w = [torch.nn.Parameter(torch.randn(11, 4)), torch.nn.Parameter(torch.randn(6))]
+    data = torch.arange(40, dtype=torch.float32).reshape(10, 4)
+    loss = ((data @ w[0][:4]).pow(2).mean() + w[1].sum() * data.mean())
+    loss.backward()
+    full = torch.cat([w[0].grad.reshape(-1), w[1].grad.reshape(-1)]).numpy()
+    assert np.allclose(res[0][1], full, rtol=1e-5, atol=1e-5)
+
+
+def test_metrics_known_values():
+    from mulut_b200.metrics import PSNR, cal_ssim, modcrop, rgb2ycbcr
+    a = np.full((32, 32), 100.0)
+    b = a + 5.0
+    assert abs(PSNR(a, b, 4) - 20 * np.log10(255 / 5)) < 1e-4
+    assert abs(cal_ssim(a, a) - 1.0) < 1e-12
+    assert modcrop(np.zeros((10, 11, 3)), 4).shape == (8, 8, 3)
+    y = rgb2ycbcr(np.array([[[255, 255, 255], [0, 0, 0]]], dtype=np.uint8))[..., 0]
+    assert np.allclose(y, [[235.0, 16.0]])
