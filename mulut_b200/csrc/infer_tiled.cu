@@ -13,9 +13,12 @@
 //       cell-major (one aligned 64-byte block per 16^4 cell = all 16 corners x 4
 //       outputs, biased to uint8).  Four adjacent lanes fetch one cell with one
 //       LDG.128 each, so a warp-level gather touches 8 cache lines instead of
-//       32; each lane weights its 4 corners branch-free
-//       (w(S) = relu(min_{i in S} f_i - max_{i not in S} f_i)) and folds them
-//       with dp4a; partial sums meet through warp shuffles.  The 2x2
+//       32.  The sample's own lane sorts the four fractions once (branch-free
+//       min/max network), packs the five simplex weights into bytes with one
+//       subtraction and names the order by an 8-bit code; each quad lane turns
+//       (code, lane) into a PRMT selector from a 2 KB shared table, so ONE PRMT
+//       yields the weights of its 4 corners, folded with dp4a; partial sums meet
+//       through warp shuffles.  The 2x2
 //       pixel-shuffle is fused into a shared-memory output tile that is stored
 //       with coalesced 16-byte writes.
 //
@@ -242,44 +245,68 @@ constexpr int Q2_RW = 4;
 constexpr int Q2_THREADS = 96 * Q2_RW;
 constexpr int Q2_OP = 2 * TWB;          // output tile pitch in bytes
 
-// weights of this lane's four corners (c,d in {00,01,10,11}) packed as bytes.
-// w(S) = relu(min_{i in S} f_i - max_{i not in S} f_i), S = corner's tap set;
-// non-zero exactly on the five path vertices of the sorted-simplex walk.
-__device__ __forceinline__ uint32_t corner_weights4(uint32_t rq, bool la, bool lb)
+// Selector table: for every descending order of the four taps (code = t0 | t1<<2 |
+// t2<<4 | t3<<6, t_k = tap with the k-th largest fraction) and every quad lane l
+// (la = l>>1, lb = l&1), a PRMT selector that picks, for the lane's four corners
+// (c,d) in {00,01,10,11}, the weight of the path vertex sitting on that corner:
+// nibble k (0..4) = "this corner is the k-th vertex of the sorted-simplex walk"
+// (bytes 0..3 of the packed weights w0..w3, byte 4 = w4), nibble 0xC = "not on the
+// path" (sign-replicate of a byte whose top bit is clear -> 0x00).
+__device__ __forceinline__ void build_selector_table(uint16_t *s_sel)
 {
-    const int fa = (rq >> 12) & 15, fb = (rq >> 8) & 15, fc = (rq >> 4) & 15, fd = rq & 15;
-    const int ain = min(la ? fa : 16, lb ? fb : 16);
-    const int aout = max(la ? 0 : fa, lb ? 0 : fb);
-    const int mn = min(fc, fd), mx = max(fc, fd);
-    const int w00 = max(ain - max(aout, mx), 0);
-    const int w01 = max(min(ain, fd) - max(aout, fc), 0);
-    const int w10 = max(min(ain, fc) - max(aout, fd), 0);
-    const int w11 = max(min(ain, mn) - aout, 0);
-    return (uint32_t)w00 | ((uint32_t)w01 << 8) | ((uint32_t)w10 << 16) | ((uint32_t)w11 << 24);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        const int code = i >> 2, l = i & 3;
+        uint32_t sel = 0;
+#pragma unroll
+        for (int cd = 0; cd < 4; ++cd) {
+            // bit t of S = tap t belongs to the corner (taps a,b,c,d = 0,1,2,3)
+            const int S = ((l >> 1) & 1) | ((l & 1) << 1) | (((cd >> 1) & 1) << 2) | ((cd & 1) << 3);
+            const int k = __popc(S);
+            int prefix = 0;
+            for (int j = 0; j < k; ++j) prefix |= 1 << ((code >> (2 * j)) & 3);
+            sel |= (uint32_t)(prefix == S ? k : 0xC) << (4 * cd);
+        }
+        s_sel[i] = (uint16_t)sel;
+    }
 }
 
 template <char MODE, int CT>
 __device__ __forceinline__ void quad_mode(const uint8_t *__restrict__ sp, int C,
-                                          const uint8_t *__restrict__ cells, int ql, bool la, bool lb,
-                                          uint32_t (&acc)[4][4])
+                                          const uint8_t *__restrict__ cells, int ql,
+                                          const uint16_t *__restrict__ s_sel_lane, uint32_t (&acc)[4][4])
 {
     constexpr int P = tile_pitch<CT>();
     const int Cc = CT > 0 ? CT : C;
+    const uint8_t *__restrict__ cells_lane = cells + ql * 16;     // my 16 B of every cell
     const uint32_t t0 = sp[0];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const uint32_t t1 = sp[tap_off(MODE, r, 1, true) * P + tap_off(MODE, r, 1, false) * Cc];
         const uint32_t t2 = sp[tap_off(MODE, r, 2, true) * P + tap_off(MODE, r, 2, false) * Cc];
         const uint32_t t3 = sp[tap_off(MODE, r, 3, true) * P + tap_off(MODE, r, 3, false) * Cc];
-        // request word: cell id (m_a m_b m_c m_d nibbles) << 16 | fractions (f_a f_b f_c f_d nibbles)
+        // ---- owner side: sort the fractions once per interpolation ----
+        uint32_t k0 = ((t0 & 15u) << 2) | 0u, k1 = ((t1 & 15u) << 2) | 1u;
+        uint32_t k2 = ((t2 & 15u) << 2) | 2u, k3 = ((t3 & 15u) << 2) | 3u;
+        sort4_desc(k0, k1, k2, k3);
+        const uint32_t K = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);
+        const uint32_t Fs = (K >> 2) & 0x0F0F0F0Fu;               // f(1)..f(4) in bytes 0..3
+        const uint32_t w0123 = ((Fs << 8) | 16u) - Fs;            // bytes: 16-f1, f1-f2, f2-f3, f3-f4 (no borrows)
+        const uint32_t code = ((K & 0x03030303u) * 0x01041040u) >> 24;   // t0 | t1<<2 | t2<<4 | t3<<6
         const uint32_t cell = ((t0 >> 4) << 12) | ((t1 >> 4) << 8) | ((t2 >> 4) << 4) | (t3 >> 4);
-        const uint32_t fr = ((t0 & 15u) << 12) | ((t1 & 15u) << 8) | ((t2 & 15u) << 4) | (t3 & 15u);
-        const uint32_t req = (cell << 16) | fr;
+        const uint32_t req = (cell << 16) | (code << 8) | (Fs >> 24);    // low byte = w4 = f(4)
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
+            // ---- quad side: fetch my 16 B of sample s's cell, weight my 4 corners ----
             const uint32_t rq = __shfl_sync(FULL, req, s, 4);
-            const uint4 d = __ldg(reinterpret_cast<const uint4 *>(cells + (size_t)(rq >> 16) * 64 + ql * 16));
-            const uint32_t wp = corner_weights4(rq, la, lb);
+            const uint32_t rw = __shfl_sync(FULL, w0123, s, 4);
+            uint64_t addr;                                        // one IMAD.WIDE instead of a 64-bit add chain
+            asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(addr) : "r"(rq >> 16), "l"(cells_lane));
+            const uint4 d = __ldg(reinterpret_cast<const uint4 *>(addr));
+            const uint32_t sel = s_sel_lane[((rq >> 8) & 0xFFu) * 4];
+            uint32_t wp;                                          // byte 4 of {rw,rq} = w4
+            // raw prmt.b32: __byte_perm() masks the selector to 3 bits per nibble and
+            // would drop the sign-replicate bit the "not on the path" nibble 0xC relies on
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(wp) : "r"(rw), "r"(rq), "r"(sel));
             acc[s][subpixel_perm<2>(r, 0)] = __dp4a(d.x, wp, acc[s][subpixel_perm<2>(r, 0)]);
             acc[s][subpixel_perm<2>(r, 1)] = __dp4a(d.y, wp, acc[s][subpixel_perm<2>(r, 1)]);
             acc[s][subpixel_perm<2>(r, 2)] = __dp4a(d.z, wp, acc[s][subpixel_perm<2>(r, 2)]);
@@ -295,7 +322,9 @@ stage_last2_quad_kernel(const __grid_constant__ StageArgs a)
     constexpr int P = tile_pitch<CT>();
     __shared__ __align__(16) uint8_t s_in[(Q2_TH + 4) * P];
     __shared__ __align__(16) uint8_t s_out[2 * Q2_TH * Q2_OP];
+    __shared__ uint16_t s_sel[1024];
 
+    build_selector_table(s_sel);                 // published by the first __syncthreads below
     const int C = CT > 0 ? CT : a.C;
     const int WC = a.W * C;
     const int tiles_x = (WC + TWB - 1) / TWB;
@@ -335,9 +364,9 @@ stage_last2_quad_kernel(const __grid_constant__ StageArgs a)
             for (int m = 0; m < a.n_modes; ++m) {
                 const uint8_t *__restrict__ cells = a.lut_alt[m];
                 switch (a.modes[m]) {
-                case 's': quad_mode<'s', CT>(sp, C, cells, ql, la, lb, acc); break;
-                case 'd': quad_mode<'d', CT>(sp, C, cells, ql, la, lb, acc); break;
-                default: quad_mode<'y', CT>(sp, C, cells, ql, la, lb, acc); break;
+                case 's': quad_mode<'s', CT>(sp, C, cells, ql, s_sel + ql, acc); break;
+                case 'd': quad_mode<'d', CT>(sp, C, cells, ql, s_sel + ql, acc); break;
+                default: quad_mode<'y', CT>(sp, C, cells, ql, s_sel + ql, acc); break;
                 }
             }
             // quad butterfly: lane ql ends with the complete sums of sample slot ql

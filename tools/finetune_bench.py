@@ -1,0 +1,123 @@
+#!/usr/bin/env python
+"""cfg4 benchmark: one LUT fine-tuning step (MuLUT.forward + mse_loss + backward +
+LUT-gradient all-reduce + Adam), batch 256 of 48x48 patches, x4 sdy 2-stage, shipped
+LUTs.  One process per GPU (torchrun); the batch is split across ranks.
+
+    python tools/finetune_bench.py [--batch 256] [--steps 10] [--aten]
+
+--aten additionally times the plain-ATen restatement of the reference's torch path
+(oracle/interp_torch_oracle.py) on the same GPU: the bar the kernels replace.
+Prints one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def shipped_luts():
+    d = os.path.join(ROOT, "tests", "golden", "luts_x4")
+    return {"s{}_{}".format(s, m): np.load(os.path.join(d, "LUT_ft_x4_4bit_int8_s{}_{}.npy".format(s, m))).reshape(
+        -1, 1 if s == 1 else 16) for s in (1, 2) for m in "sdy"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=256, help="GLOBAL batch (split across ranks)")
+    ap.add_argument("--crop", type=int, default=48)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--aten", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    from mulut_b200.dist import FlatGradBucket
+    from mulut_b200.cli.finetune_lut import lr_lambda, synthetic_batch
+    from mulut_b200.model import MuLUT
+
+    dev = torch.device("cuda", local)
+    luts = shipped_luts()
+    net = MuLUT(None, 2, ["s", "d", "y"], upscale=4, interval=4, luts=luts).to(dev)
+    params = list(net.parameters())
+    bucket = FlatGradBucket(params)
+    opt = torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lr_lambda(200000, 1e-3, 1e-4))
+    per_rank = args.batch // world
+    im, lb = synthetic_batch(per_rank, args.crop, 4, 1000 + rank, dev)
+
+    def step(timers=None):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        bucket.zero_()
+        ev[0].record()
+        pred = net(im)
+        loss = F.mse_loss(pred, lb)
+        ev[1].record()
+        loss.backward()
+        ev[2].record()
+        bucket.all_reduce_mean()
+        ev[3].record()
+        opt.step()
+        sched.step()
+        ev[4].record()
+        if timers is not None:
+            torch.cuda.synchronize()
+            for i, k in enumerate(("fwd", "bwd", "allreduce", "adam")):
+                timers[k] += ev[i].elapsed_time(ev[i + 1])
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    timers = {"fwd": 0.0, "bwd": 0.0, "allreduce": 0.0, "adam": 0.0}
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss = step(timers)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res = {"workload": "cfg4 finetune step, global batch {} of {}x{} patches, x4 sdy 2-stage".format(args.batch, args.crop, args.crop),
+           "n_gpus": world, "ms_per_step": float(t.item()) * 1e3, "patches_per_s": args.batch / float(t.item()),
+           "breakdown_ms": {k: v / args.steps for k, v in timers.items()}, "loss": float(loss.item()),
+           "allreduce_bytes": bucket.flat.numel() * 4}
+
+    if args.aten and rank == 0:
+        from oracle import interp_torch_oracle as TO
+        ws = {k: torch.tensor(v.astype(np.float32) / 127.0, device=dev, requires_grad=True) for k, v in luts.items()}
+        b = min(per_rank, 32)
+        for _ in range(2):
+            pred = TO.mulut_forward(ws, im[:b], 2, "sdy", 4)
+            F.mse_loss(pred, lb[:b]).backward()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 3
+        for _ in range(n):
+            pred = TO.mulut_forward(ws, im[:b], 2, "sdy", 4)
+            F.mse_loss(pred, lb[:b]).backward()
+        torch.cuda.synchronize()
+        res["aten_restatement"] = {"batch": b, "ms_fwd_bwd": (time.perf_counter() - t0) / n * 1e3,
+                                   "note": "sorted-simplex ATen restatement of sr/model.py (oracle), same GPU; the "
+                                           "reference's 24-mask version is slower still"}
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
