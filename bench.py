@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="mulut_b200", choices=["mulut_b200", "reference"])
     ap.add_argument("--frames", type=int, default=16, help="1080p frames per GPU per step")
-    ap.add_argument("--kernel", type=str, default="auto", choices=["auto", "generic", "tiled"])
+    ap.add_argument("--kernel", type=str, default="auto", choices=["auto", "generic", "tiled", "quad", "cell"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -199,7 +199,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 
-    kernel = {"auto": _lib.KERNEL_AUTO, "generic": _lib.KERNEL_GENERIC, "tiled": _lib.KERNEL_TILED}[args.kernel]
+    kernel = {"auto": _lib.KERNEL_AUTO, "generic": _lib.KERNEL_GENERIC, "tiled": _lib.KERNEL_TILED,
+              "quad": _lib.KERNEL_TILED_QUAD, "cell": _lib.KERNEL_TILED_CELL}[args.kernel]
     luts = make_luts()
     eng = LutEngine(luts, STAGES, MODES, SCALE, INTERVAL, device=local, kernel=kernel)
     F = args.frames

@@ -42,7 +42,9 @@ typedef struct mulut_handle_s *mulut_handle_t;
 /* Kernel selection for mulut_sr_infer_u8 (parity tests run all of them). */
 #define MULUT_KERNEL_AUTO     (-1)  /* fastest applicable */
 #define MULUT_KERNEL_GENERIC    0   /* any modes/scale/interval/C; LUTs gathered vertex-major from L2 */
-#define MULUT_KERNEL_TILED      1   /* interval 4: smem-resident stage-1 LUTs, cell-major last-stage LUTs */
+#define MULUT_KERNEL_TILED      1   /* interval 4: smem-resident up=1 LUTs, cell-major up=2 LUTs; alias of _QUAD */
+#define MULUT_KERNEL_TILED_QUAD 1   /* ... up=2 last stage: four lanes fetch one 64-B cell (K1c)          */
+#define MULUT_KERNEL_TILED_CELL 2   /* ... up=2 last stage: one lane fetches its cell, 2 x LDG.256 (K1d)  */
 
 int mulut_version(void);
 const char *mulut_last_error(void);

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmulut_b200.so")
 
 OK, E_BAD_MODE, E_BAD_ARG, E_CUDA, E_NOMEM, E_LUT_SMALL = 0, -1, -2, -3, -4, -5
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED = -1, 0, 1
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED, KERNEL_TILED_QUAD, KERNEL_TILED_CELL = -1, 0, 1, 1, 2
 
 PROF_KINDS = {"generic_stage": 0, "generic_last": 1, "smem_stage": 2, "combine": 3, "last_tiled": 4}
 

@@ -119,7 +119,10 @@ static int run_stages(mulut_handle_s *h, Workspace &w, const uint8_t *d_in, uint
         int done = 1;
         if (uses_tiled(h, up, C)) {
             int launches = 0;
-            done = launch_stage_tiled_ws(a, up, w.partial, stream, &launches, &h->prof);
+            // K1c (quad-cooperative) is the default: measured 6.83 ms vs 7.73 ms for K1d on
+            // 16 x 1080p (profiles/r01_bench_quad_vs_cell.txt); K1d only on request.
+            const bool owner_only = h->kernel == MULUT_KERNEL_TILED_CELL;
+            done = launch_stage_tiled_ws(a, up, w.partial, stream, &launches, &h->prof, owner_only);
             if (done < 0) return done;
             h->launches += launches;
         }
@@ -266,7 +269,7 @@ int mulut_destroy(mulut_handle_t h)
 
 int mulut_set_kernel(mulut_handle_t h, int kernel)
 {
-    if (!h || kernel < MULUT_KERNEL_AUTO || kernel > MULUT_KERNEL_TILED) {
+    if (!h || kernel < MULUT_KERNEL_AUTO || kernel > MULUT_KERNEL_TILED_CELL) {
         set_error("mulut_set_kernel: bad argument");
         return MULUT_E_BAD_ARG;
     }

@@ -51,8 +51,9 @@ int launch_stage_generic(const StageArgs &a, int up, cudaStream_t stream);
 // Tiled sm_100a kernels (interval 4 only).  Return MULUT_OK, an error, or
 // +1 when the configuration is not covered (caller falls back to generic).
 // partial: workspace of n_modes * N*H*W*C int16 (used when up == 1).
+// owner_only selects K1d (one lane per sample) over K1c (quad-cooperative) for the up = 2 last stage.
 int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStream_t stream, int *launches,
-                          Prof *prof);
+                          Prof *prof, bool owner_only);
 bool tiled_supported(int up, int interval, int n_modes);
 
 // Device-side LUT re-layouts (run once at mulut_create).

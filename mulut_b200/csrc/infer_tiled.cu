@@ -245,6 +245,30 @@ constexpr int Q2_RW = 4;
 constexpr int Q2_THREADS = 96 * Q2_RW;
 constexpr int Q2_OP = 2 * TWB;          // output tile pitch in bytes
 
+// coalesced copy-out of the (2*TH) x (2*TWB) byte output tile (pixel-shuffle already applied)
+__device__ __forceinline__ void store_out_tile(const uint8_t *s_out, uint8_t *__restrict__ out, int n, int H, int oWC,
+                                               int y0, int X0)
+{
+    uint8_t *__restrict__ outn = out + (size_t)n * (2 * H) * oWC;
+    const int oy0 = 2 * y0, oX0 = 2 * X0;
+    const int rows_valid = min(2 * Q2_TH, 2 * H - oy0);
+    const int cols_valid = min(Q2_OP, oWC - oX0);
+    const bool vec_ok = ((oWC & 15) == 0) && ((reinterpret_cast<uintptr_t>(outn) & 15) == 0) && (cols_valid == Q2_OP);
+    if (vec_ok) {
+        constexpr int VPR = Q2_OP / 16;    // 12 vectors per row
+        for (int idx = threadIdx.x; idx < rows_valid * VPR; idx += blockDim.x) {
+            const int r = idx / VPR, c16 = idx - r * VPR;
+            const uint4 v = *reinterpret_cast<const uint4 *>(s_out + r * Q2_OP + c16 * 16);
+            *reinterpret_cast<uint4 *>(outn + (size_t)(oy0 + r) * oWC + oX0 + c16 * 16) = v;
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < rows_valid * Q2_OP; idx += blockDim.x) {
+            const int r = idx / Q2_OP, c = idx - r * Q2_OP;
+            if (c < cols_valid) outn[(size_t)(oy0 + r) * oWC + oX0 + c] = s_out[r * Q2_OP + c];
+        }
+    }
+}
+
 // Selector table: for every descending order of the four taps (code = t0 | t1<<2 |
 // t2<<4 | t3<<6, t_k = tap with the k-th largest fraction) and every quad lane l
 // (la = l>>1, lb = l&1), a PRMT selector that picks, for the lane's four corners
@@ -322,7 +346,7 @@ stage_last2_quad_kernel(const __grid_constant__ StageArgs a)
     constexpr int P = tile_pitch<CT>();
     __shared__ __align__(16) uint8_t s_in[(Q2_TH + 4) * P];
     __shared__ __align__(16) uint8_t s_out[2 * Q2_TH * Q2_OP];
-    __shared__ uint16_t s_sel[1024];
+    __shared__ __align__(8) uint16_t s_sel[1024];
 
     build_selector_table(s_sel);                 // published by the first __syncthreads below
     const int C = CT > 0 ? CT : a.C;
@@ -394,26 +418,133 @@ stage_last2_quad_kernel(const __grid_constant__ StageArgs a)
         }
         __syncthreads();
 
-        // coalesced copy-out of the (2*TH) x (2*TWB) byte tile
-        uint8_t *__restrict__ outn = a.out + (size_t)n * (2 * a.H) * oWC;
-        const int oy0 = 2 * y0, oX0 = 2 * X0;
-        const int rows_valid = min(2 * Q2_TH, 2 * a.H - oy0);
-        const int cols_valid = min(Q2_OP, oWC - oX0);
-        const bool vec_ok = ((oWC & 15) == 0) && ((reinterpret_cast<uintptr_t>(outn) & 15) == 0) &&
-                            (cols_valid == Q2_OP);
-        if (vec_ok) {
-            constexpr int VPR = Q2_OP / 16;    // 12 vectors per row
-            for (int idx = threadIdx.x; idx < rows_valid * VPR; idx += blockDim.x) {
-                const int r = idx / VPR, c16 = idx - r * VPR;
-                const uint4 v = *reinterpret_cast<const uint4 *>(s_out + r * Q2_OP + c16 * 16);
-                *reinterpret_cast<uint4 *>(outn + (size_t)(oy0 + r) * oWC + oX0 + c16 * 16) = v;
-            }
-        } else {
-            for (int idx = threadIdx.x; idx < rows_valid * Q2_OP; idx += blockDim.x) {
-                const int r = idx / Q2_OP, c = idx - r * Q2_OP;
-                if (c < cols_valid) outn[(size_t)(oy0 + r) * oWC + oX0 + c] = s_out[r * Q2_OP + c];
-            }
+        store_out_tile(s_out, a.out, n, a.H, oWC, y0, X0);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1d: last stage, up = 2, cell-major LUT, one lane per sample ("owner-only").
+// The sample's lane fetches its whole 64-byte cell with two 256-bit loads
+// (LDG.E.256: the a=0 and a=1 halves), builds the four per-row weight words with
+// four PRMTs from one 8-byte selector fetch and folds 16 dp4a.  No shuffles, no
+// cross-lane reduction: ~40 % fewer instructions than K1c, but MEASURED SLOWER on
+// B200 (7.73 ms vs 6.83 ms per 16 x 1080p): a 256-bit load whose 32 lanes touch 32
+// different lines costs ~1 L1 cycle per lane even on hits, so the L1 data pipe, not
+// the ALU, bounds it.  Kept as a selectable cross-check (MULUT_KERNEL_TILED_CELL).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void ldg256(const uint8_t *p, uint32_t (&w)[8])
+{
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+template <char MODE, int CT>
+__device__ __forceinline__ void cell_mode(const uint8_t *__restrict__ sp, int C, const uint8_t *__restrict__ cells,
+                                          const uint16_t *__restrict__ s_sel, uint32_t (&acc)[4])
+{
+    constexpr int P = tile_pitch<CT>();
+    const int Cc = CT > 0 ? CT : C;
+    const uint32_t t0 = sp[0];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t t1 = sp[tap_off(MODE, r, 1, true) * P + tap_off(MODE, r, 1, false) * Cc];
+        const uint32_t t2 = sp[tap_off(MODE, r, 2, true) * P + tap_off(MODE, r, 2, false) * Cc];
+        const uint32_t t3 = sp[tap_off(MODE, r, 3, true) * P + tap_off(MODE, r, 3, false) * Cc];
+        uint32_t k0 = ((t0 & 15u) << 2) | 0u, k1 = ((t1 & 15u) << 2) | 1u;
+        uint32_t k2 = ((t2 & 15u) << 2) | 2u, k3 = ((t3 & 15u) << 2) | 3u;
+        sort4_desc(k0, k1, k2, k3);
+        const uint32_t K = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);
+        const uint32_t Fs = (K >> 2) & 0x0F0F0F0Fu;               // f(1)..f(4) in bytes 0..3
+        const uint32_t w0123 = ((Fs << 8) | 16u) - Fs;            // bytes: 16-f1, f1-f2, f2-f3, f3-f4
+        const uint32_t w4 = Fs >> 24;                             // f(4)
+        const uint32_t code = ((K & 0x03030303u) * 0x01041040u) >> 24;
+        const uint32_t cell = ((t0 >> 4) << 12) | ((t1 >> 4) << 8) | ((t2 >> 4) << 4) | (t3 >> 4);
+        uint64_t addr;
+        asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(addr) : "r"(cell), "l"(cells));
+        uint32_t A0[8], A1[8];
+        ldg256(reinterpret_cast<const uint8_t *>(addr), A0);       // rows (a,b) = 00, 01
+        ldg256(reinterpret_cast<const uint8_t *>(addr) + 32, A1);  // rows (a,b) = 10, 11
+        const uint2 sel = *reinterpret_cast<const uint2 *>(s_sel + code * 4);   // selectors of rows 0..3
+        const uint32_t wp0 = prmt(w0123, w4, sel.x), wp1 = prmt(w0123, w4, sel.x >> 16);
+        const uint32_t wp2 = prmt(w0123, w4, sel.y), wp3 = prmt(w0123, w4, sel.y >> 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t v = acc[subpixel_perm<2>(r, j)];
+            v = __dp4a(A0[j], wp0, v);
+            v = __dp4a(A0[4 + j], wp1, v);
+            v = __dp4a(A1[j], wp2, v);
+            v = __dp4a(A1[4 + j], wp3, v);
+            acc[subpixel_perm<2>(r, j)] = v;
         }
+    }
+}
+
+template <int CT>
+__global__ void __launch_bounds__(Q2_THREADS, 2)
+stage_last2_cell_kernel(const __grid_constant__ StageArgs a)
+{
+    constexpr int P = tile_pitch<CT>();
+    __shared__ __align__(16) uint8_t s_in[(Q2_TH + 4) * P];
+    __shared__ __align__(16) uint8_t s_out[2 * Q2_TH * Q2_OP];
+    __shared__ __align__(8) uint16_t s_sel[1024];
+
+    build_selector_table(s_sel);                 // published by the first __syncthreads below
+    const int C = CT > 0 ? CT : a.C;
+    const int WC = a.W * C;
+    const int tiles_x = (WC + TWB - 1) / TWB;
+    const int tiles_y = (a.H + Q2_TH - 1) / Q2_TH;
+    const long long n_tiles = (long long)a.N * tiles_y * tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lx = (warp % 3) * 32 + lane;
+    const int rp = warp / 3;
+    const int ocol0 = lx + C * (lx / C);
+    const int cols = TWB + 4 * C;
+    const int oWC = 2 * WC;
+    const uint32_t bias_total = (uint32_t)a.n_modes * 4u * 2048u;
+    const uint32_t den = 16u * a.n_modes;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tx = (int)(tile % tiles_x);
+        const long long tr = tile / tiles_x;
+        const int ty = (int)(tr % tiles_y);
+        const int n = (int)(tr / tiles_y);
+        const int y0 = ty * Q2_TH, X0 = tx * TWB;
+        const uint8_t *__restrict__ img = a.in + (size_t)n * a.H * WC;
+
+        __syncthreads();
+        fill_tile(s_in, P, Q2_TH + 4, cols, img, a.H, C, WC, y0, X0);
+        __syncthreads();
+
+#pragma unroll 1
+        for (int ly = rp; ly < Q2_TH; ly += Q2_RW) {
+            const uint8_t *sp = s_in + (ly + 2) * P + lx + 2 * C;
+            uint32_t acc[4] = {0u, 0u, 0u, 0u};
+            for (int m = 0; m < a.n_modes; ++m) {
+                const uint8_t *__restrict__ cells = a.lut_alt[m];
+                switch (a.modes[m]) {
+                case 's': cell_mode<'s', CT>(sp, C, cells, s_sel, acc); break;
+                case 'd': cell_mode<'d', CT>(sp, C, cells, s_sel, acc); break;
+                default: cell_mode<'y', CT>(sp, C, cells, s_sel, acc); break;
+                }
+            }
+            uint8_t *so = s_out + (2 * ly) * Q2_OP + ocol0;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const int S = (int)acc[u * 2 + v] - (int)bias_total;
+                    so[u * Q2_OP + v * C] = (uint8_t)rhe_div_clamp_u8(S, den);
+                }
+        }
+        __syncthreads();
+        store_out_tile(s_out, a.out, n, a.H, oWC, y0, X0);
     }
 }
 
@@ -498,23 +629,29 @@ static int launch_smem_stage(const StageArgs &a, int16_t *partial, cudaStream_t 
 }
 
 template <int CT>
-static int launch_quad_stage(const StageArgs &a, cudaStream_t stream)
+static int launch_quad_stage(const StageArgs &a, bool owner_only, cudaStream_t stream)
 {
     int per_sm = 0;
-    MULUT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_last2_quad_kernel<CT>, Q2_THREADS, 0));
+    if (owner_only)
+        MULUT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_last2_cell_kernel<CT>, Q2_THREADS, 0));
+    else
+        MULUT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_last2_quad_kernel<CT>, Q2_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     const int WC = a.W * a.C;
     const long long n_tiles = (long long)a.N * ((a.H + Q2_TH - 1) / Q2_TH) * ((WC + TWB - 1) / TWB);
     long long grid = (long long)per_sm * a.num_sms;
     if (grid > n_tiles) grid = n_tiles;
-    stage_last2_quad_kernel<CT><<<(unsigned)grid, Q2_THREADS, 0, stream>>>(a);
+    if (owner_only)
+        stage_last2_cell_kernel<CT><<<(unsigned)grid, Q2_THREADS, 0, stream>>>(a);
+    else
+        stage_last2_quad_kernel<CT><<<(unsigned)grid, Q2_THREADS, 0, stream>>>(a);
     MULUT_CUDA(cudaGetLastError());
     return MULUT_OK;
 }
 
 // partial: workspace of n_modes * N*H*W*C int16 (only used for up == 1)
 int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStream_t stream, int *launches,
-                          Prof *prof)
+                          Prof *prof, bool owner_only)
 {
     const size_t total = (size_t)a.N * a.H * a.W * a.C;
     if (total == 0) return MULUT_OK;
@@ -539,9 +676,9 @@ int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStre
     }
     if (!a.last) return 1;
     prof->begin(MULUT_PROF_LAST_TILED, stream);
-    int rc = a.C == 3 ? launch_quad_stage<3>(a, stream)
-           : a.C == 1 ? launch_quad_stage<1>(a, stream)
-                      : launch_quad_stage<0>(a, stream);
+    int rc = a.C == 3 ? launch_quad_stage<3>(a, owner_only, stream)
+           : a.C == 1 ? launch_quad_stage<1>(a, owner_only, stream)
+                      : launch_quad_stage<0>(a, owner_only, stream);
     prof->end(stream);
     if (rc) return rc;
     *launches += 1;
