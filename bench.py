@@ -33,9 +33,34 @@ WORKLOAD = "cfg2: sr_x2sdy 2-stage, 1920x1080x3 uint8 -> 3840x2160x3, scale 2, r
 # algorithmic bytes per input sample (SURVEY.md 8d / DESIGN.md): 12*5 vertex rows of 1 B in
 # stage 1, 12*5 rows of r^2 = 4 B in stage 2; HBM: 1 B read + r^2 written.
 GATHER_B_STAGE1, GATHER_B_STAGE2, HBM_B = 60, 240, 5
+SHIPPED_LUTS = False
+
+# The headline (and the default) is cfg2; the other BASELINE.json configs can be timed with --config.
+CONFIGS = {
+    "cfg2": dict(H=1080, W=1920, scale=2, shipped=False, frames=16,
+                 name="cfg2: sr_x2sdy 2-stage, 1920x1080x3 uint8 -> 3840x2160x3, scale 2, random int8 LUTs (seed 1)"),
+    "cfg1": dict(H=256, W=256, scale=4, shipped=True, frames=64,
+                 name="cfg1: sr_x2sdy 2-stage, 256x256x3 -> 1024x1024x3, scale 4, shipped LUTs"),
+    "cfg3": dict(H=540, W=960, scale=4, shipped=True, frames=16,
+                 name="cfg3: sr_x4sdy 2-stage, 960x540x3 -> 3840x2160x3, scale 4, shipped LUTs"),
+    "cfg5": dict(H=4320, W=7680, scale=2, shipped=False, frames=2,
+                 name="cfg5: sr_x2sdy 2-stage, 7680x4320x3 -> 15360x8640x3, scale 2, random int8 LUTs (seed 1)"),
+}
+
+
+def select_config(name):
+    global H, W, SCALE, WORKLOAD, GATHER_B_STAGE2, HBM_B, SHIPPED_LUTS
+    c = CONFIGS[name]
+    H, W, SCALE, WORKLOAD, SHIPPED_LUTS = c["H"], c["W"], c["scale"], c["name"], c["shipped"]
+    GATHER_B_STAGE2, HBM_B = 60 * SCALE * SCALE, 1 + SCALE * SCALE
+    return c["frames"]
 
 
 def make_luts(seed=1):
+    if SHIPPED_LUTS:                       # the reference's x4 tables (tests/golden/luts_x4)
+        d = os.path.join(ROOT, "tests", "golden", "luts_x4")
+        return {"s{}_{}".format(s, m): np.load(os.path.join(d, "LUT_ft_x4_4bit_int8_s{}_{}.npy".format(s, m))).reshape(
+            -1, 1 if s == 1 else 16) for s in (1, 2) for m in "sdy"}
     rng = np.random.default_rng(seed)
     luts = {}
     for s in range(STAGES):
@@ -172,12 +197,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="mulut_b200", choices=["mulut_b200", "reference"])
-    ap.add_argument("--frames", type=int, default=16, help="1080p frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: per config, 16 for cfg2)")
+    ap.add_argument("--config", type=str, default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--kernel", type=str, default="auto", choices=["auto", "generic", "tiled", "quad", "cell"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    default_frames = select_config(args.config)
+    if args.frames <= 0:
+        args.frames = default_frames
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

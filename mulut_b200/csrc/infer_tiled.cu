@@ -245,26 +245,28 @@ constexpr int Q2_RW = 4;
 constexpr int Q2_THREADS = 96 * Q2_RW;
 constexpr int Q2_OP = 2 * TWB;          // output tile pitch in bytes
 
-// coalesced copy-out of the (2*TH) x (2*TWB) byte output tile (pixel-shuffle already applied)
+// coalesced copy-out of the (UP*TH) x (UP*TWB) byte output tile (pixel-shuffle already applied)
+template <int UP>
 __device__ __forceinline__ void store_out_tile(const uint8_t *s_out, uint8_t *__restrict__ out, int n, int H, int oWC,
                                                int y0, int X0)
 {
-    uint8_t *__restrict__ outn = out + (size_t)n * (2 * H) * oWC;
-    const int oy0 = 2 * y0, oX0 = 2 * X0;
-    const int rows_valid = min(2 * Q2_TH, 2 * H - oy0);
-    const int cols_valid = min(Q2_OP, oWC - oX0);
-    const bool vec_ok = ((oWC & 15) == 0) && ((reinterpret_cast<uintptr_t>(outn) & 15) == 0) && (cols_valid == Q2_OP);
+    constexpr int OP = UP * TWB;
+    uint8_t *__restrict__ outn = out + (size_t)n * (UP * H) * oWC;
+    const int oy0 = UP * y0, oX0 = UP * X0;
+    const int rows_valid = min(UP * Q2_TH, UP * H - oy0);
+    const int cols_valid = min(OP, oWC - oX0);
+    const bool vec_ok = ((oWC & 15) == 0) && ((reinterpret_cast<uintptr_t>(outn) & 15) == 0) && (cols_valid == OP);
     if (vec_ok) {
-        constexpr int VPR = Q2_OP / 16;    // 12 vectors per row
+        constexpr int VPR = OP / 16;
         for (int idx = threadIdx.x; idx < rows_valid * VPR; idx += blockDim.x) {
             const int r = idx / VPR, c16 = idx - r * VPR;
-            const uint4 v = *reinterpret_cast<const uint4 *>(s_out + r * Q2_OP + c16 * 16);
+            const uint4 v = *reinterpret_cast<const uint4 *>(s_out + r * OP + c16 * 16);
             *reinterpret_cast<uint4 *>(outn + (size_t)(oy0 + r) * oWC + oX0 + c16 * 16) = v;
         }
     } else {
-        for (int idx = threadIdx.x; idx < rows_valid * Q2_OP; idx += blockDim.x) {
-            const int r = idx / Q2_OP, c = idx - r * Q2_OP;
-            if (c < cols_valid) outn[(size_t)(oy0 + r) * oWC + oX0 + c] = s_out[r * Q2_OP + c];
+        for (int idx = threadIdx.x; idx < rows_valid * OP; idx += blockDim.x) {
+            const int r = idx / OP, c = idx - r * OP;
+            if (c < cols_valid) outn[(size_t)(oy0 + r) * oWC + oX0 + c] = s_out[r * OP + c];
         }
     }
 }
@@ -418,7 +420,7 @@ stage_last2_quad_kernel(const __grid_constant__ StageArgs a)
         }
         __syncthreads();
 
-        store_out_tile(s_out, a.out, n, a.H, oWC, y0, X0);
+        store_out_tile<2>(s_out, a.out, n, a.H, oWC, y0, X0);
     }
 }
 
@@ -544,7 +546,171 @@ stage_last2_cell_kernel(const __grid_constant__ StageArgs a)
                 }
         }
         __syncthreads();
-        store_out_tile(s_out, a.out, n, a.H, oWC, y0, X0);
+        store_out_tile<2>(s_out, a.out, n, a.H, oWC, y0, X0);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1e: last stage, up = 4, cell-major LUT (256 B per cell), quad-cooperative.
+// A cell = 4 row-blocks l = (a,b) of 64 B; a row-block = 16 words, word = the four
+// (c,d) corners of ONE output column (dp4a operand).  The 16 output columns are
+// stored in ROTATION-ORBIT order: lane q of the quad owns orbit q of the 4x4
+// sub-pixel block, (u,v) -> (v,3-u) walks an orbit, so for rotation r the word i of
+// a lane lands on the lane's own position (i+r)&3: static register indexing, no
+// cross-lane reduction.  Per interpolation the quad fetches the 3 row-blocks the
+// simplex walk can touch (rows 00 and 11, and 10 or 01 depending on whether tap a
+// or tap b has the larger fraction): 3 x (4 lanes x LDG.128).
+//   byte[cell*256 + l*64 + q*16 + i*4 + cd] = LUT[v(l,cd)][col(q,i)] + 128
+// ---------------------------------------------------------------------------
+__host__ __device__ constexpr int orbit_col(int q, int i)
+{
+    int u = q == 3 ? 1 : 0, v = q == 3 ? 1 : q;        // orbit starts (0,0),(0,1),(0,2),(1,1)
+    for (int k = 0; k < i; ++k) { int t = u; u = v; v = 3 - t; }
+    return u * 4 + v;
+}
+
+__global__ void build_cell_major4_kernel(const int8_t *__restrict__ lut, uint8_t *__restrict__ cells)
+{
+    const size_t total = (size_t)65536 * 256;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int cd = idx & 3, i = (idx >> 2) & 3, q = (idx >> 4) & 3, l = (idx >> 6) & 3;
+        const int cell = (int)(idx >> 8);
+        const int ma = cell >> 12, mb = (cell >> 8) & 15, mc = (cell >> 4) & 15, md = cell & 15;
+        const int v = (ma + (l >> 1)) * 4913 + (mb + (l & 1)) * 289 + (mc + (cd >> 1)) * 17 + (md + (cd & 1));
+        int u = q == 3 ? 1 : 0, w = q == 3 ? 1 : q;
+        for (int k = 0; k < i; ++k) { int t = u; u = w; w = 3 - t; }
+        cells[idx] = (uint8_t)((int)lut[(size_t)v * 16 + u * 4 + w] + 128);
+    }
+}
+
+constexpr int Q4_OP = 4 * TWB;
+
+template <char MODE, int CT>
+__device__ __forceinline__ void quad4_mode(const uint8_t *__restrict__ sp, int C,
+                                           const uint8_t *__restrict__ cells_lane,
+                                           const uint16_t *__restrict__ s_sel, uint32_t (&acc)[4][4])
+{
+    constexpr int P = tile_pitch<CT>();
+    const int Cc = CT > 0 ? CT : C;
+    const uint32_t t0 = sp[0];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t t1 = sp[tap_off(MODE, r, 1, true) * P + tap_off(MODE, r, 1, false) * Cc];
+        const uint32_t t2 = sp[tap_off(MODE, r, 2, true) * P + tap_off(MODE, r, 2, false) * Cc];
+        const uint32_t t3 = sp[tap_off(MODE, r, 3, true) * P + tap_off(MODE, r, 3, false) * Cc];
+        uint32_t k0 = ((t0 & 15u) << 2) | 0u, k1 = ((t1 & 15u) << 2) | 1u;
+        uint32_t k2 = ((t2 & 15u) << 2) | 2u, k3 = ((t3 & 15u) << 2) | 3u;
+        sort4_desc(k0, k1, k2, k3);
+        const uint32_t K = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);
+        const uint32_t Fs = (K >> 2) & 0x0F0F0F0Fu;
+        const uint32_t w0123 = ((Fs << 8) | 16u) - Fs;
+        const uint32_t code = ((K & 0x03030303u) * 0x01041040u) >> 24;
+        const uint32_t cell = ((t0 >> 4) << 12) | ((t1 >> 4) << 8) | ((t2 >> 4) << 4) | (t3 >> 4);
+        const uint32_t req = (cell << 16) | (code << 8) | (Fs >> 24);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const uint32_t rq = __shfl_sync(FULL, req, s, 4);
+            const uint32_t rw = __shfl_sync(FULL, w0123, s, 4);
+            const uint2 sel = *reinterpret_cast<const uint2 *>(s_sel + ((rq >> 8) & 0xFFu) * 4);
+            // row 01 is off the path (all nibbles 0xC) exactly when tap a precedes tap b: then use row 10
+            const bool a_first = (sel.x >> 16) == 0xCCCCu;
+            const uint32_t selm = a_first ? sel.y : (sel.x >> 16);
+            uint64_t addr;
+            asm("mad.wide.u32 %0, %1, 256, %2;" : "=l"(addr) : "r"(rq >> 16), "l"(cells_lane));
+            const uint8_t *cp = reinterpret_cast<const uint8_t *>(addr);
+            const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(cp));
+            const uint4 dm = __ldg(reinterpret_cast<const uint4 *>(cp + (a_first ? 128 : 64)));
+            const uint4 d3 = __ldg(reinterpret_cast<const uint4 *>(cp + 192));
+            const uint32_t wp0 = prmt(rw, rq, sel.x), wpm = prmt(rw, rq, selm), wp3 = prmt(rw, rq, sel.y >> 16);
+            const uint32_t x0[4] = {d0.x, d0.y, d0.z, d0.w}, xm[4] = {dm.x, dm.y, dm.z, dm.w}, x3[4] = {d3.x, d3.y, d3.z, d3.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint32_t v = acc[s][(i + r) & 3];
+                v = __dp4a(x0[i], wp0, v);
+                v = __dp4a(xm[i], wpm, v);
+                v = __dp4a(x3[i], wp3, v);
+                acc[s][(i + r) & 3] = v;
+            }
+        }
+    }
+}
+
+template <int CT>
+__global__ void __launch_bounds__(Q2_THREADS, 2)
+stage_last4_quad_kernel(const __grid_constant__ StageArgs a)
+{
+    constexpr int P = tile_pitch<CT>();
+    extern __shared__ __align__(16) uint8_t q4_smem[];
+    uint8_t *s_out = q4_smem;                                  // 4*TH x 4*TWB bytes
+    uint8_t *s_in = q4_smem + 4 * Q2_TH * Q4_OP;
+    __shared__ __align__(8) uint16_t s_sel[1024];
+
+    build_selector_table(s_sel);
+    const int C = CT > 0 ? CT : a.C;
+    const int WC = a.W * C;
+    const int tiles_x = (WC + TWB - 1) / TWB;
+    const int tiles_y = (a.H + Q2_TH - 1) / Q2_TH;
+    const long long n_tiles = (long long)a.N * tiles_y * tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lx = (warp % 3) * 32 + lane;
+    const int rp = warp / 3;
+    const int ql = lane & 3;
+    const int cols = TWB + 4 * C;
+    const int oWC = 4 * WC;
+    const uint32_t bias_total = (uint32_t)a.n_modes * 4u * 2048u;
+    const uint32_t den = 16u * a.n_modes;
+    // my orbit's four sub-pixel positions (u,v), in rotation order
+    int pu[4], pv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int u = ql == 3 ? 1 : 0, v = ql == 3 ? 1 : ql;
+        for (int k = 0; k < i; ++k) { int t = u; u = v; v = 3 - t; }
+        pu[i] = u; pv[i] = v;
+    }
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tx = (int)(tile % tiles_x);
+        const long long tr = tile / tiles_x;
+        const int ty = (int)(tr % tiles_y);
+        const int n = (int)(tr / tiles_y);
+        const int y0 = ty * Q2_TH, X0 = tx * TWB;
+        const uint8_t *__restrict__ img = a.in + (size_t)n * a.H * WC;
+
+        __syncthreads();
+        fill_tile(s_in, P, Q2_TH + 4, cols, img, a.H, C, WC, y0, X0);
+        __syncthreads();
+
+#pragma unroll 1
+        for (int ly = rp; ly < Q2_TH; ly += Q2_RW) {
+            const uint8_t *sp = s_in + (ly + 2) * P + lx + 2 * C;
+            uint32_t acc[4][4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[s][j] = 0u;
+            for (int m = 0; m < a.n_modes; ++m) {
+                const uint8_t *__restrict__ cells_lane = a.lut_alt[m] + ql * 16;
+                switch (a.modes[m]) {
+                case 's': quad4_mode<'s', CT>(sp, C, cells_lane, s_sel, acc); break;
+                case 'd': quad4_mode<'d', CT>(sp, C, cells_lane, s_sel, acc); break;
+                default: quad4_mode<'y', CT>(sp, C, cells_lane, s_sel, acc); break;
+                }
+            }
+            // lane ql holds orbit ql of the 4x4 block of each of the quad's four samples
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int sx = (lx & ~3) + s;                          // local byte column of sample s
+                uint8_t *so = s_out + (4 * ly) * Q4_OP + sx + 3 * C * (sx / C);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int S = (int)acc[s][i] - (int)bias_total;
+                    so[pu[i] * Q4_OP + pv[i] * C] = (uint8_t)rhe_div_clamp_u8(S, den);
+                }
+            }
+        }
+        __syncthreads();
+        store_out_tile<4>(s_out, a.out, n, a.H, oWC, y0, X0);
     }
 }
 
@@ -572,6 +738,7 @@ size_t cell_major_bytes(int up)
 {
     if (up == 1) return LUT1_SMEM;
     if (up == 2) return (size_t)65536 * 64;
+    if (up == 4) return (size_t)65536 * 256;
     return 0;
 }
 
@@ -587,12 +754,17 @@ int build_cell_major(const int8_t *d_lut, uint8_t *d_alt, int up, cudaStream_t s
         MULUT_CUDA(cudaGetLastError());
         return MULUT_OK;
     }
+    if (up == 4) {
+        build_cell_major4_kernel<<<2048, 256, 0, stream>>>(d_lut, d_alt);
+        MULUT_CUDA(cudaGetLastError());
+        return MULUT_OK;
+    }
     return MULUT_OK;
 }
 
 bool tiled_supported(int up, int interval, int n_modes)
 {
-    return interval == 4 && n_modes >= 1 && (up == 1 || up == 2);
+    return interval == 4 && n_modes >= 1 && (up == 1 || up == 2 || up == 4);
 }
 
 // ---------------------------------------------------------------------------
@@ -649,6 +821,27 @@ static int launch_quad_stage(const StageArgs &a, bool owner_only, cudaStream_t s
     return MULUT_OK;
 }
 
+template <int CT>
+static int launch_quad4_stage(const StageArgs &a, cudaStream_t stream)
+{
+    constexpr int P = tile_pitch<CT>();
+    const size_t smem = (size_t)4 * Q2_TH * Q4_OP + (size_t)(Q2_TH + 4) * P;
+    {
+        int rc = set_smem(stage_last4_quad_kernel<CT>, smem);
+        if (rc) return rc;
+    }
+    int per_sm = 0;
+    MULUT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_last4_quad_kernel<CT>, Q2_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int WC = a.W * a.C;
+    const long long n_tiles = (long long)a.N * ((a.H + Q2_TH - 1) / Q2_TH) * ((WC + TWB - 1) / TWB);
+    long long grid = (long long)per_sm * a.num_sms;
+    if (grid > n_tiles) grid = n_tiles;
+    stage_last4_quad_kernel<CT><<<(unsigned)grid, Q2_THREADS, smem, stream>>>(a);
+    MULUT_CUDA(cudaGetLastError());
+    return MULUT_OK;
+}
+
 // partial: workspace of n_modes * N*H*W*C int16 (only used for up == 1)
 int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStream_t stream, int *launches,
                           Prof *prof, bool owner_only)
@@ -676,7 +869,13 @@ int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStre
     }
     if (!a.last) return 1;
     prof->begin(MULUT_PROF_LAST_TILED, stream);
-    int rc = a.C == 3 ? launch_quad_stage<3>(a, owner_only, stream)
+    int rc;
+    if (up == 4)
+        rc = a.C == 3 ? launch_quad4_stage<3>(a, stream)
+           : a.C == 1 ? launch_quad4_stage<1>(a, stream)
+                      : launch_quad4_stage<0>(a, stream);
+    else
+        rc = a.C == 3 ? launch_quad_stage<3>(a, owner_only, stream)
            : a.C == 1 ? launch_quad_stage<1>(a, owner_only, stream)
                       : launch_quad_stage<0>(a, owner_only, stream);
     prof->end(stream);
