@@ -43,14 +43,19 @@ CONFIGS = {
                  name="cfg1: sr_x2sdy 2-stage, 256x256x3 -> 1024x1024x3, scale 4, shipped LUTs"),
     "cfg3": dict(H=540, W=960, scale=4, shipped=True, frames=16,
                  name="cfg3: sr_x4sdy 2-stage, 960x540x3 -> 3840x2160x3, scale 4, shipped LUTs"),
+    # calibration workload (not a BASELINE config): the x2 last stage ALONE on uniform frames,
+    # i.e. all eight value bins equally populated - the worst case of the binned kernel
+    "x2s1": dict(H=1080, W=1920, scale=2, shipped=False, frames=16, stages=1,
+                 name="x2s1: ONE-stage sr_x2sdy, 1920x1080x3 uniform uint8 -> 3840x2160x3, random int8 LUTs"),
     "cfg5": dict(H=4320, W=7680, scale=2, shipped=False, frames=2,
                  name="cfg5: sr_x2sdy 2-stage, 7680x4320x3 -> 15360x8640x3, scale 2, random int8 LUTs (seed 1)"),
 }
 
 
 def select_config(name):
-    global H, W, SCALE, WORKLOAD, GATHER_B_STAGE2, HBM_B, SHIPPED_LUTS
+    global H, W, SCALE, WORKLOAD, GATHER_B_STAGE2, HBM_B, SHIPPED_LUTS, STAGES
     c = CONFIGS[name]
+    STAGES = c.get("stages", 2)
     H, W, SCALE, WORKLOAD, SHIPPED_LUTS = c["H"], c["W"], c["scale"], c["name"], c["shipped"]
     GATHER_B_STAGE2, HBM_B = 60 * SCALE * SCALE, 1 + SCALE * SCALE
     return c["frames"]
@@ -199,7 +204,7 @@ def main():
     ap.add_argument("--impl", type=str, default="mulut_b200", choices=["mulut_b200", "reference"])
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: per config, 16 for cfg2)")
     ap.add_argument("--config", type=str, default="cfg2", choices=sorted(CONFIGS))
-    ap.add_argument("--kernel", type=str, default="auto", choices=["auto", "generic", "tiled", "quad", "cell"])
+    ap.add_argument("--kernel", type=str, default="auto", choices=["auto", "generic", "tiled", "quad", "cell", "binned"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -229,7 +234,8 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 
     kernel = {"auto": _lib.KERNEL_AUTO, "generic": _lib.KERNEL_GENERIC, "tiled": _lib.KERNEL_TILED,
-              "quad": _lib.KERNEL_TILED_QUAD, "cell": _lib.KERNEL_TILED_CELL}[args.kernel]
+              "quad": _lib.KERNEL_TILED_QUAD, "cell": _lib.KERNEL_TILED_CELL,
+              "binned": _lib.KERNEL_TILED_BINNED}[args.kernel]
     luts = make_luts()
     eng = LutEngine(luts, STAGES, MODES, SCALE, INTERVAL, device=local, kernel=kernel)
     F = args.frames
@@ -299,9 +305,9 @@ def main():
     hbm_peak, peak_src = measured_peaks()
     dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, (0.0, 0))
     dom_name, (dom_ms, dom_n) = dom
-    gather_b = {"last_tiled": GATHER_B_STAGE2, "generic_last": GATHER_B_STAGE2, "smem_stage": GATHER_B_STAGE1,
+    gather_b = {"last_tiled": GATHER_B_STAGE2, "last_binned": GATHER_B_STAGE2, "generic_last": GATHER_B_STAGE2, "smem_stage": GATHER_B_STAGE1,
                 "generic_stage": GATHER_B_STAGE1, "combine": 0}.get(dom_name, 0)
-    hbm_b = {"last_tiled": 1 + SCALE * SCALE, "generic_last": 1 + SCALE * SCALE, "smem_stage": 1 + 2 * len(MODES),
+    hbm_b = {"last_tiled": 1 + SCALE * SCALE, "last_binned": 1 + SCALE * SCALE, "generic_last": 1 + SCALE * SCALE, "smem_stage": 1 + 2 * len(MODES),
              "generic_stage": 2, "combine": 2 * len(MODES) + 1}.get(dom_name, HBM_B)
     per_launch_s = dom_ms * 1e-3 / max(dom_n, 1)
     traffic = None

@@ -45,6 +45,9 @@ typedef struct mulut_handle_s *mulut_handle_t;
 #define MULUT_KERNEL_TILED      1   /* interval 4: smem-resident up=1 LUTs, cell-major up=2 LUTs; alias of _QUAD */
 #define MULUT_KERNEL_TILED_QUAD 1   /* ... up=2 last stage: four lanes fetch one 64-B cell (K1c)          */
 #define MULUT_KERNEL_TILED_CELL 2   /* ... up=2 last stage: one lane fetches its cell, 2 x LDG.256 (K1d)  */
+#define MULUT_KERNEL_TILED_BINNED 3 /* ... up=2 last stage: samples binned by value, LUT slabs in shared
+                                       memory, TMA tile ring (K1f); needs 16-B aligned frames with
+                                       W*C % 16 == 0 and C in {1,3}, otherwise runs K1c              */
 
 int mulut_version(void);
 const char *mulut_last_error(void);
@@ -96,7 +99,10 @@ long long mulut_launch_count(mulut_handle_t handle);
 #define MULUT_PROF_SMEM_STAGE     2   /* stage_smem_kernel (K1a)              */
 #define MULUT_PROF_COMBINE        3   /* combine_kernel (K1b)                 */
 #define MULUT_PROF_LAST_TILED     4   /* tiled last-stage kernel (K1c)        */
-#define MULUT_PROF_KINDS          5
+#define MULUT_PROF_BIN_HIST       5   /* K1f preparation: histogram, plan, orphan list */
+#define MULUT_PROF_LAST_BINNED    6   /* stage_last2_binned_kernel (K1f)               */
+#define MULUT_PROF_BIN_ORPHANS    7   /* stage_generic_list_kernel: K1f's sparse bins  */
+#define MULUT_PROF_KINDS          8
 int mulut_profile_enable(mulut_handle_t handle, int on);
 int mulut_profile_read(mulut_handle_t handle, int kind, double *total_ms, long long *launches);
 

@@ -32,6 +32,9 @@ struct Workspace {
     size_t img_bytes = 0;
     int16_t *partial = nullptr;             // per-mode int16 planes of the smem-LUT kernel
     size_t partial_bytes = 0;
+    void *bn_ctl = nullptr;                 // control block of the binned kernel (histogram, plan)
+    uint32_t *bn_list = nullptr;            // its orphan-sample list
+    size_t bn_list_cap = 0;
 };
 
 }  // namespace mulut
@@ -46,6 +49,7 @@ struct mulut_handle_s {
     size_t lut_bytes = 0;
     const int8_t *lut[MULUT_MAX_STAGES][MULUT_MAX_MODES] = {};
     const uint8_t *lut_alt[MULUT_MAX_STAGES][MULUT_MAX_MODES] = {};
+    const uint8_t *lut_slab[MULUT_MAX_MODES] = {};   // last stage, up = 2 only
     TapTable taps;
     Workspace ws[1 + HOST_LANES];           // [0] device API, [1..] host-path lanes
     cudaStream_t lane_stream[HOST_LANES] = {};
@@ -55,7 +59,8 @@ struct mulut_handle_s {
     Prof prof;
 };
 
-static int ws_reserve(Workspace &w, int stages, int n_modes, size_t frame_samples, bool want_partial)
+static int ws_reserve(Workspace &w, int stages, int n_modes, size_t frame_samples, bool want_partial,
+                      bool want_binned = false)
 {
     if (stages > 1 && w.img_bytes < frame_samples) {
         for (int i = 0; i < 2; ++i) { cudaFree(w.img[i]); w.img[i] = nullptr; }
@@ -71,12 +76,21 @@ static int ws_reserve(Workspace &w, int stages, int n_modes, size_t frame_sample
         MULUT_CUDA(cudaMalloc(&w.partial, need));
         w.partial_bytes = need;
     }
+    if (want_binned) {
+        if (!w.bn_ctl) MULUT_CUDA(cudaMalloc(&w.bn_ctl, binned_ctl_bytes()));
+        const size_t cap = frame_samples / 4 + 1024;       // the plan keeps the orphan list below this
+        if (w.bn_list_cap < cap) {
+            cudaFree(w.bn_list); w.bn_list = nullptr; w.bn_list_cap = 0;
+            MULUT_CUDA(cudaMalloc(&w.bn_list, cap * sizeof(uint32_t)));
+            w.bn_list_cap = cap;
+        }
+    }
     return MULUT_OK;
 }
 
 static void ws_free(Workspace &w)
 {
-    cudaFree(w.img[0]); cudaFree(w.img[1]); cudaFree(w.partial);
+    cudaFree(w.img[0]); cudaFree(w.img[1]); cudaFree(w.partial); cudaFree(w.bn_ctl); cudaFree(w.bn_list);
     w = Workspace();
 }
 
@@ -97,7 +111,8 @@ static int run_stages(mulut_handle_s *h, Workspace &w, const uint8_t *d_in, uint
         const int up = last ? h->scale : 1;
         if (up == 1 && uses_tiled(h, up, C)) want_partial = true;
     }
-    int rc = ws_reserve(w, h->stages, h->n_modes, samples, want_partial);
+    const bool want_binned = h->scale == 2 && h->interval == 4 && h->kernel != MULUT_KERNEL_GENERIC;
+    int rc = ws_reserve(w, h->stages, h->n_modes, samples, want_partial, want_binned);
     if (rc) return rc;
 
     const uint8_t *cur = d_in;
@@ -113,11 +128,21 @@ static int run_stages(mulut_handle_s *h, Workspace &w, const uint8_t *d_in, uint
         for (int m = 0; m < h->n_modes; ++m) {
             a.lut[m] = h->lut[s][m];
             a.lut_alt[m] = h->lut_alt[s][m];
+            a.lut_slab[m] = last ? h->lut_slab[m] : nullptr;
             a.modes[m] = h->modes[m];
         }
         a.taps = h->taps;
         int done = 1;
-        if (uses_tiled(h, up, C)) {
+        // K1f (binned, shared-memory slabs) when forced, or on AUTO for launches big enough to
+        // amortise one 177 KB LUT load per SM; it falls through to K1c when TMA cannot map the frames.
+        if (uses_tiled(h, up, C) && binned_supported(a, up) &&
+            (h->kernel == MULUT_KERNEL_TILED_BINNED || (h->kernel == MULUT_KERNEL_AUTO && samples >= (1u << 20)))) {
+            int launches = 0;
+            done = launch_stage_binned(a, w.bn_ctl, w.bn_list, w.bn_list_cap, stream, &launches, &h->prof);
+            if (done < 0) return done;
+            h->launches += launches;
+        }
+        if (done == 1 && uses_tiled(h, up, C)) {
             int launches = 0;
             // K1c (quad-cooperative) is the default: measured 6.83 ms vs 7.73 ms for K1d on
             // 16 x 1080p (profiles/r01_bench_quad_vs_cell.txt); K1d only on request.
@@ -196,6 +221,9 @@ int mulut_create(mulut_handle_t *handle, int device, int stages, const char *mod
         const size_t ab = interval == 4 ? cell_major_bytes(up) : 0;
         for (int m = 0; m < n_modes; ++m) { alt_off[s][m] = off; off += align256(ab); }
     }
+    const bool want_slabs = interval == 4 && scale == 2;
+    size_t slab_off[MULUT_MAX_MODES];
+    for (int m = 0; m < n_modes && want_slabs; ++m) { slab_off[m] = off; off += align256(slab_major_bytes()); }
     h->lut_bytes = off;
     e = cudaMalloc(&h->d_luts, off);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(luts)", __FILE__, __LINE__); }
@@ -212,6 +240,11 @@ int mulut_create(mulut_handle_t *handle, int device, int stages, const char *mod
                 uint8_t *alt = h->d_luts + alt_off[s][m];
                 rc = build_cell_major(dst, alt, up, 0);
                 h->lut_alt[s][m] = alt;
+            }
+            if (!rc && want_slabs && s + 1 == stages) {
+                uint8_t *sl = h->d_luts + slab_off[m];
+                rc = build_slab_major(dst, sl, 0);
+                h->lut_slab[m] = sl;
             }
         }
     }
@@ -269,7 +302,7 @@ int mulut_destroy(mulut_handle_t h)
 
 int mulut_set_kernel(mulut_handle_t h, int kernel)
 {
-    if (!h || kernel < MULUT_KERNEL_AUTO || kernel > MULUT_KERNEL_TILED_CELL) {
+    if (!h || kernel < MULUT_KERNEL_AUTO || kernel > MULUT_KERNEL_TILED_BINNED) {
         set_error("mulut_set_kernel: bad argument");
         return MULUT_E_BAD_ARG;
     }
@@ -324,7 +357,8 @@ int mulut_reserve(mulut_handle_t h, int N, int H, int W, int C)
     int rc = check_shape(h, (void *)1, (void *)1, N, H, W, C);
     if (rc) return rc;
     MULUT_CUDA(cudaSetDevice(h->device));
-    return ws_reserve(h->ws[0], h->stages, h->n_modes, (size_t)N * H * W * C, h->interval == 4);
+    return ws_reserve(h->ws[0], h->stages, h->n_modes, (size_t)N * H * W * C, h->interval == 4,
+                      h->scale == 2 && h->interval == 4);
 }
 
 int mulut_sr_infer_u8(mulut_handle_t h, const uint8_t *d_in, uint8_t *d_out, int N, int H, int W, int C,

@@ -15,6 +15,7 @@ struct StageArgs {
     int num_sms;
     const int8_t *lut[MULUT_MAX_MODES];      // reference layout: int8 (L^4, up^2)
     const uint8_t *lut_alt[MULUT_MAX_MODES]; // device re-layout used by the tiled kernels
+    const uint8_t *lut_slab[MULUT_MAX_MODES];// slab-major biased re-layout of an up = 2 table (binned kernel), or null
     char modes[MULUT_MAX_MODES];
     TapTable taps;
 };
@@ -55,6 +56,17 @@ int launch_stage_generic(const StageArgs &a, int up, cudaStream_t stream);
 int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStream_t stream, int *launches,
                           Prof *prof, bool owner_only);
 bool tiled_supported(int up, int interval, int n_modes);
+
+// K1f, the binned shared-memory kernel for the up = 2 last stage (infer_binned.cu).
+// binned_supported: configuration + TMA preconditions (16-byte aligned frames, W*C % 16 == 0).
+// launch_stage_binned returns MULUT_OK, an error (< 0) or +1 (not applicable: caller falls back).
+// ctl: binned_ctl_bytes() of device workspace; list: list_cap uint32 entries (orphan samples), may be null.
+bool binned_supported(const StageArgs &a, int up);
+int launch_stage_binned(const StageArgs &a, void *ctl, uint32_t *list, size_t list_cap, cudaStream_t stream,
+                        int *launches, Prof *prof);
+size_t binned_ctl_bytes();
+size_t slab_major_bytes();
+int build_slab_major(const int8_t *d_lut_vertex_major, uint8_t *d_slabs, cudaStream_t stream);
 
 // Device-side LUT re-layouts (run once at mulut_create).
 //  cell-major: for each of the 16^4 cells, the 16 corner rows laid out so one

@@ -1,0 +1,551 @@
+// K1f: last stage, up = 2, LUT slabs resident in SHARED MEMORY ("binned" kernel).
+//
+// Tap a of every one of a sample's 12 interpolations (3 modes x 4 rotations) is
+// the sample itself (sr/4_test_lut.py:18-51: tap a has offset (0,0) in every
+// mode), so all 60 vertex rows a sample can touch lie in the LUT slabs
+// a in {m_a, m_a + 1}, m_a = sample >> 4.  The 17 slabs of a x2 table are 19.6 KB
+// each: three of them for each of three modes fit one SM's shared memory
+// (3 x 3 x 19 664 B = 177 KB).  So the kernel splits the samples by value instead
+// of by position:
+//
+//   * bin b = sample >> 5 (8 bins); a persistent CTA serves ONE bin and keeps
+//     slabs 2b .. 2b+2 of every mode in shared memory (one TMA bulk copy each);
+//   * CTAs are dealt to the bins in proportion to a cost model fed by an 8-bin
+//     histogram of the stage input (bin_hist_kernel), computed identically by
+//     every CTA - no host round trip;
+//   * every CTA of a bin walks its share of the halo'd tiles, which arrive through
+//     a ring of TMA tensor-tile loads (cp.async.bulk.tensor.3d + mbarrier, zero
+//     fill outside the frame patched to replicate padding in shared memory);
+//   * a scan compacts the tile's samples of this bin into a queue (ballot/popc);
+//     full rounds of BN_THREADS queue entries are interpolated, the remainder is
+//     carried to the next tile while its ring slot is still resident;
+//   * per interpolation: keys f<<28 | byte-stride are sorted by a 5-comparator
+//     min/max network, the vertex chain is v0, v0+s1, v0+s1+s2, v4-s4, v4 with
+//     v4 = v0 + (sum of strides), five LDS.32 fetch the biased rows (4 outputs in
+//     one word) and two multiply-adds per row accumulate all four outputs:
+//     even bytes in a 32-bit lane pair, the whole word in a 64-bit accumulator
+//     (fields overlap; the even lanes are subtracted at the end);
+//   * the 2x2 pixel-shuffle is fused into four byte stores per sample (L2 merges
+//     the partial sectors written by the CTAs of different bins).
+//
+// Gather cost: 5 LDS.32 per interpolation at the shared-memory bank-conflict rate
+// (~10 lanes/clk/SM) instead of one 64-byte L1/L2 cell per interpolation.
+// Arithmetic follows SURVEY.md 8-SPEC (sr/4_test_lut.py:14-237, :279-306).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "infer.cuh"
+#include "tma.cuh"
+
+namespace mulut {
+
+constexpr int BN_TW = 96;                       // tile width, byte columns (multiple of C for C <= 4)
+constexpr int BN_TH = 32;                       // tile rows
+constexpr int BN_HX = 16;                       // box column of the tile's first sample: TMA needs the box to
+                                                // start on a 16-byte boundary, so the left halo (2*C <= 16 B)
+                                                // is fetched as a whole 16-byte granule
+constexpr int BN_BOXW = 128;                    // HX + TW + 2*C rounded up to 16 B (C <= 4)
+constexpr int BN_BOXH = BN_TH + 4;
+constexpr int BN_SLOT = BN_BOXW * BN_BOXH;      // 4608 B per ring slot, 128-B aligned
+constexpr int BN_RING = 8;
+constexpr int BN_AHEAD = 3;                     // TMA prefetch distance in tiles
+constexpr int BN_CARRY = BN_RING - BN_AHEAD - 1;   // tiles a queue entry may outlive its scan
+constexpr int BN_THREADS = 768;
+constexpr int BN_QCAP = 8192;                   // queue capacity: power of two > (THREADS - 1 + TW*TH) + TW*TH
+constexpr int BN_SLAB_WORDS = 4916;             // 17^3 = 4913 rows, padded so a slab is a 16-B multiple
+constexpr int BN_SLAB_BYTES = BN_SLAB_WORDS * 4;
+constexpr int BN_BIN_BYTES = 3 * BN_SLAB_BYTES; // slabs 2b, 2b+1, 2b+2 of one mode
+constexpr int BN_MAX_MODES = 3;
+constexpr int BN_BINS = 8;
+constexpr size_t BN_SMEM = (size_t)BN_RING * BN_SLOT + BN_QCAP * 2 + (size_t)BN_MAX_MODES * BN_BIN_BYTES;
+
+static_assert(BN_TW / 4 * BN_TH == BN_THREADS, "scan mapping: one 4-sample word per thread");
+static_assert(BN_QCAP >= BN_THREADS + 2 * BN_TW * BN_TH, "queue too small");
+static_assert(BN_HX + BN_TW + 2 * 4 <= BN_BOXW && 2 * 4 <= BN_HX, "box too narrow for C <= 4");
+
+size_t slab_major_bytes() { return (size_t)17 * BN_SLAB_BYTES; }
+
+// byte[(a*4916 + b*289 + c*17 + d)*4 + j] = LUT[a*17^3 + b*17^2 + c*17 + d][j] + 128
+__global__ void build_slab_major2_kernel(const int8_t *__restrict__ lut, uint8_t *__restrict__ slabs)
+{
+    const int total = 17 * BN_SLAB_BYTES;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int w = i >> 2, j = i & 3;
+        const int a = w / BN_SLAB_WORDS, rem = w - a * BN_SLAB_WORDS;
+        slabs[i] = rem < 4913 ? (uint8_t)((int)lut[((size_t)a * 4913 + rem) * 4 + j] + 128) : (uint8_t)0;
+    }
+}
+
+int build_slab_major(const int8_t *d_lut, uint8_t *d_slabs, cudaStream_t stream)
+{
+    build_slab_major2_kernel<<<256, 256, 0, stream>>>(d_lut, d_slabs);
+    MULUT_CUDA(cudaGetLastError());
+    return MULUT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// control block (device, 256 B, zeroed before every launch) and the three small
+// kernels that prepare a launch: histogram -> plan -> orphan list
+// ---------------------------------------------------------------------------
+struct BinCtl {
+    unsigned long long hist[BN_BINS];   // samples per bin (sample >> 5)
+    int g[BN_BINS];                     // CTAs dealt to each bin; 0 = bin not resident
+    uint32_t orphan_mask;               // bins left to the L2-gather list kernel
+    uint32_t list_count;                // orphan samples collected
+};
+static_assert(sizeof(BinCtl) <= 256, "control block");
+size_t binned_ctl_bytes() { return 256; }
+
+__global__ void __launch_bounds__(256)
+bin_hist_kernel(const uint8_t *__restrict__ img, size_t total, BinCtl *__restrict__ ctl)
+{
+    unsigned long long *__restrict__ hist = ctl->hist;
+    uint32_t cnt[BN_BINS];
+#pragma unroll
+    for (int b = 0; b < BN_BINS; ++b) cnt[b] = 0;
+    const size_t n16 = total / 16;
+    const uint4 *__restrict__ v = reinterpret_cast<const uint4 *>(img);
+    unsigned long long packed = 0;
+    int pending = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 q = __ldg(v + i);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) packed += 1ull << (((w[k] >> (8 * e + 5)) & 7u) * 8);
+        if (++pending == 15) {                 // 240 samples: no 8-bit field can overflow
+#pragma unroll
+            for (int b = 0; b < BN_BINS; ++b) cnt[b] += (uint32_t)(packed >> (8 * b)) & 0xFFu;
+            packed = 0;
+            pending = 0;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < BN_BINS; ++b) cnt[b] += (uint32_t)(packed >> (8 * b)) & 0xFFu;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (size_t i = n16 * 16; i < total; ++i) {
+            const uint32_t bb = img[i] >> 5;
+#pragma unroll
+            for (int b = 0; b < BN_BINS; ++b) cnt[b] += (bb == (uint32_t)b);
+        }
+#pragma unroll
+    for (int b = 0; b < BN_BINS; ++b) {
+        uint32_t c = cnt[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(hist + b, (unsigned long long)c);
+    }
+}
+
+// Plan (one thread): which bins get shared-memory CTAs, how many, and which are "orphans".
+// A bin is worth a resident CTA group only if its samples outweigh the fixed cost of
+// walking every tile once more (scan + barriers); sparse bins go to a list that the
+// generic L2-gather kernel finishes (stage_generic_list_kernel).  Costs in SM cycles.
+constexpr unsigned long long BN_CV = 1000;      // per tile visit of one CTA
+constexpr unsigned long long BN_CS = 8;         // per sample interpolated from shared memory
+constexpr unsigned long long BN_CG = 26;        // per sample interpolated by the list kernel
+__global__ void bin_plan_kernel(BinCtl *__restrict__ ctl, long long n_tiles, int G, unsigned long long list_cap,
+                                int allow_orphans)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long n[BN_BINS], cost[BN_BINS], total = 0, orph = 0;
+    bool res[BN_BINS];
+    for (int b = 0; b < BN_BINS; ++b) {
+        n[b] = ctl->hist[b];
+        res[b] = n[b] > 0 && (!allow_orphans || n[b] * (BN_CG - BN_CS) > (unsigned long long)n_tiles * BN_CV);
+        if (n[b] && !res[b]) orph += n[b];
+    }
+    while (orph > list_cap) {                               // the list is bounded: promote the largest orphan bin
+        int best = -1;
+        for (int b = 0; b < BN_BINS; ++b)
+            if (n[b] && !res[b] && (best < 0 || n[b] > n[best])) best = b;
+        res[best] = true;
+        orph -= n[best];
+    }
+    uint32_t mask = 0;
+    for (int b = 0; b < BN_BINS; ++b) {
+        cost[b] = res[b] ? (unsigned long long)n_tiles * BN_CV + n[b] * BN_CS : 0ull;
+        total += cost[b];
+        if (n[b] && !res[b]) mask |= 1u << b;
+    }
+    int g[BN_BINS], used = 0;
+    for (int b = 0; b < BN_BINS; ++b) {
+        g[b] = cost[b] ? max(1, (int)(cost[b] * (unsigned long long)G / total)) : 0;
+        used += g[b];
+    }
+    while (total && used < G) {                             // hand the rest to the most loaded groups
+        int best = -1;
+        for (int b = 0; b < BN_BINS; ++b)
+            if (g[b] && (best < 0 || cost[b] * g[best] > cost[best] * g[b])) best = b;
+        ++g[best]; ++used;
+    }
+    while (used > G) {
+        int best = -1;
+        for (int b = 0; b < BN_BINS; ++b)
+            if (g[b] > 1 && (best < 0 || cost[b] * g[best] < cost[best] * g[b])) best = b;
+        if (best < 0) break;
+        --g[best]; --used;
+    }
+    for (int b = 0; b < BN_BINS; ++b) ctl->g[b] = g[b];
+    ctl->orphan_mask = mask;
+}
+
+// Orphan list: linear indices of the samples whose bin has no resident CTAs.
+__global__ void __launch_bounds__(256)
+bin_collect_kernel(const uint8_t *__restrict__ img, size_t total, BinCtl *__restrict__ ctl, uint32_t *__restrict__ list)
+{
+    const uint32_t mask = ctl->orphan_mask;
+    if (!mask) return;
+    const size_t n16 = total / 16;
+    const uint4 *__restrict__ v = reinterpret_cast<const uint4 *>(img);
+    const int lane = threadIdx.x & 31;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n16; i0 += stride) {
+        const size_t i = i0 + lane;
+        uint32_t hits = 0;
+        if (i < n16) {
+            const uint4 q = __ldg(v + i);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) hits |= ((mask >> ((w[k] >> (8 * e + 5)) & 7u)) & 1u) << (4 * k + e);
+        }
+        const uint32_t cnt = __popc(hits);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t base = 0;
+        if (lane == 31 && incl) base = atomicAdd(&ctl->list_count, incl);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        uint32_t pos = base + incl - cnt;
+        while (hits) {
+            const int e = __ffs(hits) - 1;
+            hits &= hits - 1;
+            list[pos++] = (uint32_t)(i * 16 + e);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (size_t i = n16 * 16; i < total; ++i)
+            if ((mask >> (img[i] >> 5)) & 1u) list[atomicAdd(&ctl->list_count, 1u)] = (uint32_t)i;
+}
+
+// ---------------------------------------------------------------------------
+// the interpolation body: one mode, four rotations, LUT rows from shared memory
+// ---------------------------------------------------------------------------
+__host__ __device__ constexpr int bn_tap_off(char mode, int r, int k, bool want_dy)
+{
+    int dy = mode == 's' ? (k >> 1) : mode == 'd' ? 2 * (k >> 1) : (k == 0 ? 0 : k == 1 ? 1 : k == 2 ? 1 : 2);
+    int dx = mode == 's' ? (k & 1) : mode == 'd' ? 2 * (k & 1) : (k == 0 ? 0 : k == 1 ? 1 : k == 2 ? 2 : 1);
+    for (int i = 0; i < r; ++i) { int t = dy; dy = dx; dx = -t; }
+    return want_dy ? dy : dx;
+}
+
+template <char MODE, int CT>
+__device__ __forceinline__ void binned_mode(const uint8_t *__restrict__ sp, uint32_t t0,
+                                            const uint8_t *__restrict__ lut_a /* mode table + a_rel slab */,
+                                            uint32_t (&AE)[4], unsigned long long (&AO)[4])
+{
+    constexpr int P = BN_BOXW;
+    constexpr uint32_t SA = BN_SLAB_BYTES, SB = 289u * 4u, SC = 17u * 4u, SD = 4u;
+    constexpr uint32_t KM = 0x0FFFFFFFu;
+    const uint32_t k0c = (t0 << 28) | SA;          // fraction in the top nibble, byte stride below
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t t1 = sp[bn_tap_off(MODE, r, 1, true) * P + bn_tap_off(MODE, r, 1, false) * CT];
+        const uint32_t t2 = sp[bn_tap_off(MODE, r, 2, true) * P + bn_tap_off(MODE, r, 2, false) * CT];
+        const uint32_t t3 = sp[bn_tap_off(MODE, r, 3, true) * P + bn_tap_off(MODE, r, 3, false) * CT];
+        const uint32_t v0 = (t1 >> 4) * SB + (t2 >> 4) * SC + (t3 >> 4) * SD;
+        uint32_t k0 = k0c, k1 = (t1 << 28) | SB, k2 = (t2 << 28) | SC, k3 = (t3 << 28) | SD;
+        sort4_desc(k0, k1, k2, k3);
+        const uint32_t f1 = k0 >> 28, f2 = k1 >> 28, f3 = k2 >> 28, f4 = k3 >> 28;
+        const uint32_t v1 = v0 + (k0 & KM), v2 = v1 + (k1 & KM);
+        const uint32_t v4 = v0 + (SA + SB + SC + SD), v3 = v4 - (k3 & KM);
+        const uint32_t r0 = *reinterpret_cast<const uint32_t *>(lut_a + v0);
+        const uint32_t r1 = *reinterpret_cast<const uint32_t *>(lut_a + v1);
+        const uint32_t r2 = *reinterpret_cast<const uint32_t *>(lut_a + v2);
+        const uint32_t r3 = *reinterpret_cast<const uint32_t *>(lut_a + v3);
+        const uint32_t r4 = *reinterpret_cast<const uint32_t *>(lut_a + v4);
+        const uint32_t w0 = 16u - f1, w1 = f1 - f2, w2 = f2 - f3, w3 = f3 - f4, w4 = f4;
+        constexpr uint32_t EM = 0x00FF00FFu;
+        AE[r] += (r0 & EM) * w0 + (r1 & EM) * w1 + (r2 & EM) * w2 + (r3 & EM) * w3 + (r4 & EM) * w4;
+        AO[r] += (unsigned long long)r0 * w0 + (unsigned long long)r1 * w1 + (unsigned long long)r2 * w2 +
+                 (unsigned long long)r3 * w3 + (unsigned long long)r4 * w4;
+    }
+}
+
+struct BinnedArgs {
+    uint8_t *out;                            // (N, 2H, 2W, C)
+    int N, H, W, C;
+    int n_modes;
+    char modes[BN_MAX_MODES + 1];
+    const uint8_t *slabs[BN_MAX_MODES];      // slab-major biased tables
+    const BinCtl *ctl;                       // plan: CTAs per bin
+};
+
+template <int CT>
+__global__ void __launch_bounds__(BN_THREADS, 1)
+stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(128) uint8_t bn_smem[];
+    uint8_t *s_ring = bn_smem;
+    uint16_t *s_queue = reinterpret_cast<uint16_t *>(bn_smem + BN_RING * BN_SLOT);
+    uint8_t *s_lut = bn_smem + BN_RING * BN_SLOT + BN_QCAP * 2;
+    __shared__ __align__(8) uint64_t s_full[BN_RING];
+    __shared__ __align__(8) uint64_t s_lutbar;
+    __shared__ int4 s_info[BN_RING];             // n, y0, X0, border
+    __shared__ uint32_t s_cnt[2];                // entries queued by even / odd tiles (monotonic)
+    __shared__ int s_alloc[3];                   // bin, index within bin, CTAs of the bin
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int WC = a.W * CT;
+    const int tiles_x = (WC + BN_TW - 1) / BN_TW;
+    const int tiles_y = (a.H + BN_TH - 1) / BN_TH;
+    const long long n_tiles = (long long)a.N * tiles_y * tiles_x;
+
+    // ---- my bin: the plan kernel dealt g[b] CTAs to bin b (same answer in every CTA) ----
+    if (tid == 0) {
+        int g[BN_BINS];
+        for (int b = 0; b < BN_BINS; ++b) g[b] = a.ctl->g[b];
+        int idx = blockIdx.x, b = 0;
+        while (b < BN_BINS && idx >= g[b]) { idx -= g[b]; ++b; }
+        s_alloc[0] = b; s_alloc[1] = idx; s_alloc[2] = b < BN_BINS ? g[b] : 1;
+        for (int i = 0; i < BN_RING; ++i) mbar_init(smem_u32(&s_full[i]), 1);
+        mbar_init(smem_u32(&s_lutbar), 1);
+        mbar_fence_init();
+        s_cnt[0] = 0; s_cnt[1] = 0;
+    }
+    __syncthreads();
+    const int bin = s_alloc[0], me = s_alloc[1], gb = s_alloc[2];
+    if (bin >= BN_BINS || me >= n_tiles) return;
+    const int n_my = (int)((n_tiles - me + gb - 1) / gb);
+
+    auto issue = [&](int i) {                              // thread 0 only: TMA load of my i-th tile
+        const long long tile = me + (long long)i * gb;
+        const int tx = (int)(tile % tiles_x);
+        const long long tr = tile / tiles_x;
+        const int ty = (int)(tr % tiles_y), n = (int)(tr / tiles_y);
+        const int y0 = ty * BN_TH, X0 = tx * BN_TW;
+        const int slot = i % BN_RING;
+        const int border = (y0 < 2) || (y0 + BN_TH + 2 > a.H) || (X0 < 2 * CT) || (X0 + BN_TW + 2 * CT > WC);
+        s_info[slot] = make_int4(n, y0, X0, border);
+        const uint32_t bar = smem_u32(&s_full[slot]);
+        mbar_expect_tx(bar, BN_BOXW * BN_BOXH);
+        tma_load_3d(smem_u32(s_ring + slot * BN_SLOT), &tmap, X0 - BN_HX, y0 - 2, n, bar);
+    };
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        const uint32_t lb = smem_u32(&s_lutbar);
+        mbar_expect_tx(lb, (uint32_t)a.n_modes * BN_BIN_BYTES);
+        for (int m = 0; m < a.n_modes; ++m)
+            bulk_g2s(smem_u32(s_lut + m * BN_BIN_BYTES), a.slabs[m] + (size_t)bin * 2 * BN_SLAB_BYTES, BN_BIN_BYTES, lb);
+        for (int i = 0; i < BN_AHEAD && i < n_my; ++i) issue(i);
+    }
+
+    // scan mapping: the tile's TW x TH samples are TW/4 x TH = BN_THREADS words, one per thread
+    const int srow = tid / (BN_TW / 4), swc = tid - srow * (BN_TW / 4);
+    const int scan_off = (srow + 2) * BN_BOXW + BN_HX + swc * 4;
+    const uint32_t bin_pat = (uint32_t)bin * 0x01010101u;
+    const int oWC = 2 * WC;
+    const uint32_t den = 16u * a.n_modes;
+    const uint32_t magic = 0xFFFFFFFFu / den + 1u;                 // exact n / den for n < 2^16
+    const int bias_total = a.n_modes * 4 * 2048;                   // 16 * 128 per interpolation
+    uint32_t head = 0, tail = 0;
+    uint32_t seen0 = 0, seen1 = 0;                                 // s_cnt[0/1] as of my last look
+    uint32_t bound[BN_CARRY + 1];                                  // bound[k] = queue tail after the scan of tile i-k
+#pragma unroll
+    for (int k = 0; k <= BN_CARRY; ++k) bound[k] = 0;
+
+    // One block barrier per tile: [wait TMA] [patch border] [scan -> queue] [barrier] [issue TMA] [rounds].
+    // Threads drift by at most one scan: the queue holds a whole tile beyond the unconsumed entries,
+    // the two entry counters alternate, and a ring slot is re-filled only after the barrier that
+    // follows the rounds that drained it.
+    for (int i = 0; i < n_my; ++i) {
+        const int slot = i % BN_RING;
+        mbar_wait(smem_u32(&s_full[slot]), (uint32_t)(i / BN_RING) & 1u);
+        const int4 info = s_info[slot];
+        uint8_t *tile = s_ring + slot * BN_SLOT;
+        if (info.w) {
+            // replicate padding: overwrite the zero-filled out-of-frame cells with the clamped
+            // in-frame value (always inside this tile, never written by this pass, never read by the scan)
+            for (int idx = tid; idx < BN_BOXW * BN_BOXH; idx += BN_THREADS) {
+                const int r = idx / BN_BOXW, j = idx - r * BN_BOXW;
+                const int gy = info.y - 2 + r, gx = info.z - BN_HX + j;
+                const int cy = clampi(gy, 0, a.H - 1);
+                int cx = gx;
+                if (gx < 0) cx = (gx + BN_HX * CT) % CT;
+                else if (gx >= WC) cx = WC - CT + (gx % CT);
+                if (cy != gy || cx != gx) {
+                    const int j2 = cx - info.z + BN_HX;
+                    if (j2 >= 0 && j2 < BN_BOXW) tile[r * BN_BOXW + j] = tile[(cy - info.y + 2) * BN_BOXW + j2];
+                }
+            }
+        }
+
+        // ---- scan: queue the samples of my bin (4 samples = one word per thread) ----
+        {
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(tile + scan_off);
+            const bool valid = (info.y + srow < a.H) && (info.z + swc * 4 < WC);      // WC % 16 == 0: whole words
+            const uint32_t x = ((w >> 5) & 0x07070707u) ^ bin_pat;                    // byte == 0  <=>  sample in my bin
+            uint32_t m = valid ? (~(x + 0x7F7F7F7Fu) & 0x80808080u) : 0u;
+            const uint32_t cnt = __popc(m);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            uint32_t old = 0;
+            if (lane == 31 && incl)        // raw atom: nvcc would wrap atomicAdd in its own warp aggregation
+                asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(&s_cnt[i & 1])), "r"(incl) : "memory");
+            old = __shfl_sync(0xffffffffu, old, 31);
+            uint32_t pos = tail + (old - ((i & 1) ? seen1 : seen0)) + incl - cnt;
+            const uint32_t ebase = (uint32_t)(slot << 12) | (uint32_t)(srow * BN_TW + swc * 4);
+            while (m) {
+                const int b = __ffs(m) - 1;                                            // bit 7, 15, 23 or 31
+                m &= m - 1;
+                s_queue[pos & (BN_QCAP - 1)] = (uint16_t)(ebase + (b >> 3));
+                ++pos;
+            }
+        }
+        if (i == 0) mbar_wait(smem_u32(&s_lutbar), 0u);
+        __syncthreads();
+        {
+            const uint32_t c = *reinterpret_cast<volatile uint32_t *>(&s_cnt[i & 1]);
+            if (i & 1) { tail += c - seen1; seen1 = c; } else { tail += c - seen0; seen0 = c; }
+        }
+        if (tid == 0 && i + BN_AHEAD < n_my) issue(i + BN_AHEAD);
+#pragma unroll
+        for (int k = BN_CARRY; k > 0; --k) bound[k] = bound[k - 1];
+        bound[0] = tail;
+        const uint32_t must = (i + 1 == n_my) ? tail : bound[BN_CARRY];
+
+        // ---- interpolate: full rounds; a partial round only to release an old ring slot ----
+        for (;;) {
+            const uint32_t avail = tail - head;
+            uint32_t n;
+            if (avail >= BN_THREADS) n = BN_THREADS;
+            else if ((int)(must - head) > 0) n = avail;
+            else break;
+            if ((uint32_t)tid < n) {
+                const uint32_t e = s_queue[(head + tid) & (BN_QCAP - 1)];
+                const int eslot = e >> 12, s = e & 4095;
+                const int row = s / BN_TW, col = s - row * BN_TW;
+                const int4 ti = s_info[eslot];
+                const uint8_t *sp = s_ring + eslot * BN_SLOT + (row + 2) * BN_BOXW + col + BN_HX;
+                const uint32_t t0 = sp[0];
+                const int a_rel = (int)(t0 >> 4) - 2 * bin;
+                uint32_t AE[4] = {0u, 0u, 0u, 0u};
+                unsigned long long AO[4] = {0ull, 0ull, 0ull, 0ull};
+                for (int m = 0; m < a.n_modes; ++m) {
+                    const uint8_t *lut_a = s_lut + m * BN_BIN_BYTES + a_rel * BN_SLAB_BYTES;
+                    switch (a.modes[m]) {
+                    case 's': binned_mode<'s', CT>(sp, t0, lut_a, AE, AO); break;
+                    case 'd': binned_mode<'d', CT>(sp, t0, lut_a, AE, AO); break;
+                    default: binned_mode<'y', CT>(sp, t0, lut_a, AE, AO); break;
+                    }
+                }
+                // fields: AE = S0 | S2<<16;  AO - AE = S1<<8 | S3<<24 (S_j < 2^16: 12 interp x 16 x 255)
+                int S[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const unsigned long long D = AO[r] - (unsigned long long)AE[r];
+                    S[subpixel_perm<2>(r, 0)] += (int)(AE[r] & 0xFFFFu);
+                    S[subpixel_perm<2>(r, 1)] += (int)((uint32_t)(D >> 8) & 0xFFFFu);
+                    S[subpixel_perm<2>(r, 2)] += (int)(AE[r] >> 16);
+                    S[subpixel_perm<2>(r, 3)] += (int)((uint32_t)(D >> 24) & 0xFFFFu);
+                }
+                const int y = ti.y + row, xb = ti.z + col;
+                const int x = xb / CT, c = xb - x * CT;
+                uint8_t *__restrict__ op = a.out + ((size_t)ti.x * (2 * a.H) + 2 * y) * (size_t)oWC + (size_t)(2 * x) * CT + c;
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        const int val = S[u * 2 + v] - bias_total;
+                        const uint32_t nn = (uint32_t)max(val, 0);
+                        uint32_t qd = __umulhi(nn, magic);
+                        const uint32_t rm = nn - qd * den;
+                        qd += (2u * rm > den) || ((2u * rm == den) && (qd & 1u));
+                        op[(size_t)u * oWC + v * CT] = (uint8_t)min(qd, 255u);
+                    }
+            }
+            head += n;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// launcher
+// ---------------------------------------------------------------------------
+bool binned_supported(const StageArgs &a, int up)
+{
+    return up == 2 && a.last && a.interval == 4 && a.n_modes >= 1 && a.n_modes <= BN_MAX_MODES &&
+           (a.C == 1 || a.C == 3) && a.lut_slab[0] != nullptr && tma_frame_ok(a.in, a.H, a.W * a.C);
+}
+
+template <int CT>
+static int launch_binned_t(const BinnedArgs &b, const CUtensorMap &tmap, int num_sms, cudaStream_t stream)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        MULUT_CUDA(cudaFuncSetAttribute(stage_last2_binned_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)BN_SMEM));
+        attr_done = true;
+    }
+    stage_last2_binned_kernel<CT><<<num_sms, BN_THREADS, BN_SMEM, stream>>>(b, tmap);
+    MULUT_CUDA(cudaGetLastError());
+    return MULUT_OK;
+}
+
+int launch_stage_generic_list2(const StageArgs &a, const uint32_t *list, const uint32_t *count, cudaStream_t stream);
+
+// ctl: binned_ctl_bytes() of device workspace; list: list_cap uint32 entries of device workspace
+int launch_stage_binned(const StageArgs &a, void *ctl_mem, uint32_t *list, size_t list_cap, cudaStream_t stream,
+                        int *launches, Prof *prof)
+{
+    const size_t total = (size_t)a.N * a.H * a.W * a.C;
+    if (total == 0) return MULUT_OK;
+    CUtensorMap tmap;
+    if (tma_encode_frames(&tmap, a.in, a.N, a.H, a.W * a.C, BN_BOXW, BN_BOXH) != 0) return 1;   // caller falls back
+    BinCtl *ctl = static_cast<BinCtl *>(ctl_mem);
+    BinnedArgs b;
+    memset(&b, 0, sizeof b);
+    b.out = a.out; b.N = a.N; b.H = a.H; b.W = a.W; b.C = a.C; b.n_modes = a.n_modes; b.ctl = ctl;
+    for (int m = 0; m < a.n_modes; ++m) { b.modes[m] = a.modes[m]; b.slabs[m] = a.lut_slab[m]; }
+    const int WC = a.W * a.C;
+    const long long n_tiles = (long long)a.N * ((a.H + BN_TH - 1) / BN_TH) * ((WC + BN_TW - 1) / BN_TW);
+    const char *env = getenv("MULUT_BN_ORPHANS");
+    const int allow_orphans = (!env || env[0] != '0') && list && total < 0xFFFFFFFFull;
+
+    prof->begin(MULUT_PROF_BIN_HIST, stream);
+    MULUT_CUDA(cudaMemsetAsync(ctl, 0, binned_ctl_bytes(), stream));
+    size_t blocks = (total / 16 + 255) / 256 + 1;
+    if (blocks > (size_t)a.num_sms * 8) blocks = (size_t)a.num_sms * 8;
+    bin_hist_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.in, total, ctl);
+    bin_plan_kernel<<<1, 32, 0, stream>>>(ctl, n_tiles, a.num_sms, (unsigned long long)list_cap, allow_orphans);
+    if (allow_orphans) bin_collect_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.in, total, ctl, list);
+    prof->end(stream);
+    MULUT_CUDA(cudaGetLastError());
+
+    prof->begin(MULUT_PROF_LAST_BINNED, stream);
+    int rc = a.C == 3 ? launch_binned_t<3>(b, tmap, a.num_sms, stream) : launch_binned_t<1>(b, tmap, a.num_sms, stream);
+    prof->end(stream);
+    if (rc) return rc;
+    *launches += 3;
+    if (allow_orphans) {
+        prof->begin(MULUT_PROF_BIN_ORPHANS, stream);
+        rc = launch_stage_generic_list2(a, list, &ctl->list_count, stream);
+        prof->end(stream);
+        if (rc) return rc;
+        *launches += 2;
+    }
+    return MULUT_OK;
+}
+
+}  // namespace mulut

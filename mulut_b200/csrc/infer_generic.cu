@@ -31,70 +31,95 @@ __device__ __forceinline__ void load_row(const int8_t *__restrict__ p, int (&v)[
     }
 }
 
+// one sample i = ((n*H + y)*W + x)*C + c through all modes x rotations + epilogue
 template <int UP>
-__global__ void __launch_bounds__(256) stage_generic_kernel(const __grid_constant__ StageArgs a)
+__device__ __forceinline__ void generic_sample(const StageArgs &a, size_t i)
 {
     constexpr int UP2 = UP * UP;
     const int WC = a.W * a.C;
-    const size_t total = (size_t)a.N * a.H * WC;
     const int q = 1 << a.interval;
     const int L = (1 << (8 - a.interval)) + 1;
     const uint32_t stride[4] = {(uint32_t)(L * L * L), (uint32_t)(L * L), (uint32_t)L, 1u};
     constexpr uint32_t SBITS = 22, SMASK = (1u << SBITS) - 1u;   // L^3 <= 129^3 < 2^22
 
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const int xb = (int)(i % WC);
-        const size_t row = i / WC;
-        const int y = (int)(row % a.H);
-        const int n = (int)(row / a.H);
-        const int x = xb / a.C, c = xb - x * a.C;
-        const uint8_t *__restrict__ img = a.in + (size_t)n * a.H * WC;
+    const int xb = (int)(i % WC);
+    const size_t row = i / WC;
+    const int y = (int)(row % a.H);
+    const int n = (int)(row / a.H);
+    const int x = xb / a.C, c = xb - x * a.C;
+    const uint8_t *__restrict__ img = a.in + (size_t)n * a.H * WC;
 
-        int acc[UP2];
+    int acc[UP2];
 #pragma unroll
-        for (int j = 0; j < UP2; ++j) acc[j] = 0;
+    for (int j = 0; j < UP2; ++j) acc[j] = 0;
 
-        for (int m = 0; m < a.n_modes; ++m) {
-            const int8_t *__restrict__ lut = a.lut[m];
+    for (int m = 0; m < a.n_modes; ++m) {
+        const int8_t *__restrict__ lut = a.lut[m];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                uint32_t key[4];
-                uint32_t v = 0;
+        for (int r = 0; r < 4; ++r) {
+            uint32_t key[4];
+            uint32_t v = 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int yy = clampi(y + a.taps.dy[m][r][k], 0, a.H - 1);
-                    const int xx = clampi(x + a.taps.dx[m][r][k], 0, a.W - 1);
-                    const uint32_t t = img[(size_t)yy * WC + xx * a.C + c];
-                    v += (t >> a.interval) * stride[k];
-                    key[k] = ((t & (uint32_t)(q - 1)) << SBITS) | stride[k];
-                }
-                sort4_desc(key[0], key[1], key[2], key[3]);
-                const int f1 = key[0] >> SBITS, f2 = key[1] >> SBITS, f3 = key[2] >> SBITS, f4 = key[3] >> SBITS;
-                const int w[5] = {q - f1, f1 - f2, f2 - f3, f3 - f4, f4};
+            for (int k = 0; k < 4; ++k) {
+                const int yy = clampi(y + a.taps.dy[m][r][k], 0, a.H - 1);
+                const int xx = clampi(x + a.taps.dx[m][r][k], 0, a.W - 1);
+                const uint32_t t = img[(size_t)yy * WC + xx * a.C + c];
+                v += (t >> a.interval) * stride[k];
+                key[k] = ((t & (uint32_t)(q - 1)) << SBITS) | stride[k];
+            }
+            sort4_desc(key[0], key[1], key[2], key[3]);
+            const int f1 = key[0] >> SBITS, f2 = key[1] >> SBITS, f3 = key[2] >> SBITS, f4 = key[3] >> SBITS;
+            const int w[5] = {q - f1, f1 - f2, f2 - f3, f3 - f4, f4};
 #pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    int vals[UP2];
-                    load_row<UP>(lut + (size_t)v * UP2, vals);
+            for (int k = 0; k < 5; ++k) {
+                int vals[UP2];
+                load_row<UP>(lut + (size_t)v * UP2, vals);
 #pragma unroll
-                    for (int j = 0; j < UP2; ++j) acc[subpixel_perm<UP>(r, j)] += w[k] * vals[j];
-                    if (k < 4) v += key[k] & SMASK;
-                }
+                for (int j = 0; j < UP2; ++j) acc[subpixel_perm<UP>(r, j)] += w[k] * vals[j];
+                if (k < 4) v += key[k] & SMASK;
             }
         }
-
-        // epilogue, sr/4_test_lut.py:281-286,300-306
-        const uint32_t den = a.last ? (uint32_t)(q * a.n_modes) : (uint32_t)(q * a.n_modes * 4);
-        const int bias = a.last ? 0 : 127 * (int)den;
-        uint8_t *__restrict__ out = a.out + (size_t)n * a.H * UP * (size_t)WC * UP;
-#pragma unroll
-        for (int u = 0; u < UP; ++u)
-#pragma unroll
-            for (int vv = 0; vv < UP; ++vv) {
-                const uint32_t o = rhe_div_clamp_u8(acc[u * UP + vv] + bias, den);
-                out[((size_t)(y * UP + u) * (a.W * UP) + (x * UP + vv)) * a.C + c] = (uint8_t)o;
-            }
     }
+
+    // epilogue, sr/4_test_lut.py:281-286,300-306
+    const uint32_t den = a.last ? (uint32_t)(q * a.n_modes) : (uint32_t)(q * a.n_modes * 4);
+    const int bias = a.last ? 0 : 127 * (int)den;
+    uint8_t *__restrict__ out = a.out + (size_t)n * a.H * UP * (size_t)WC * UP;
+#pragma unroll
+    for (int u = 0; u < UP; ++u)
+#pragma unroll
+        for (int vv = 0; vv < UP; ++vv) {
+            const uint32_t o = rhe_div_clamp_u8(acc[u * UP + vv] + bias, den);
+            out[((size_t)(y * UP + u) * (a.W * UP) + (x * UP + vv)) * a.C + c] = (uint8_t)o;
+        }
+}
+
+template <int UP>
+__global__ void __launch_bounds__(256) stage_generic_kernel(const __grid_constant__ StageArgs a)
+{
+    const size_t total = (size_t)a.N * a.H * a.W * a.C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x)
+        generic_sample<UP>(a, i);
+}
+
+// The same per-sample path over an explicit list of sample indices whose length lives
+// on the device (the "orphan" samples the binned kernel K1f leaves to L2 gathers).
+template <int UP>
+__global__ void __launch_bounds__(256)
+stage_generic_list_kernel(const __grid_constant__ StageArgs a, const uint32_t *__restrict__ list,
+                          const uint32_t *__restrict__ count)
+{
+    const uint32_t total = *count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+        generic_sample<UP>(a, (size_t)list[i]);
+}
+
+int launch_stage_generic_list2(const StageArgs &a, const uint32_t *list, const uint32_t *count, cudaStream_t stream)
+{
+    stage_generic_list_kernel<2><<<(unsigned)a.num_sms * 8, 256, 0, stream>>>(a, list, count);
+    MULUT_CUDA(cudaGetLastError());
+    return MULUT_OK;
 }
 
 int launch_stage_generic(const StageArgs &a, int up, cudaStream_t stream)

@@ -1,0 +1,135 @@
+"""K1f (binned shared-memory last stage, TMA tile ring) against the C oracle.
+
+The kernel needs TMA-mappable frames (16-byte aligned, W*C % 16 == 0, C in {1,3});
+every case here satisfies that and asserts through the per-kernel profile counters
+that K1f is the kernel that actually ran."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as CO
+from oracle import mulut_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(eng, frames):
+    import torch
+    eng.profile(True)
+    out = eng(torch.from_numpy(np.ascontiguousarray(frames)).cuda()).cpu().numpy()
+    prof = eng.profile_read()
+    eng.profile(False)
+    assert "last_binned" in prof and "last_tiled" not in prof, prof
+    return out
+
+
+@pytest.mark.parametrize("C,shape", [(3, (1, 64, 96)), (3, (2, 35, 80)), (3, (3, 97, 208)), (3, (1, 1, 16)),
+                                     (3, (1, 2, 16)), (3, (1, 130, 32)), (1, (2, 67, 96)), (1, (1, 33, 208)),
+                                     (1, (1, 5, 16)), (3, (1, 200, 400))])
+@pytest.mark.parametrize("orphans", ["1", "0"])
+def test_binned_matches_oracle(C, shape, orphans, monkeypatch):
+    """orphans=0 keeps every non-empty bin in shared memory (small frames would otherwise be
+    finished entirely by the orphan list kernel)."""
+    from mulut_b200.infer import LutEngine
+    monkeypatch.setenv("MULUT_BN_ORPHANS", orphans)
+    N, H, W = shape
+    rng = np.random.default_rng(H * 1000 + W + C)
+    luts = O.random_luts(77 + C, 2, "sdy", 2)
+    frames = rng.integers(0, 256, (N, H, W, C), dtype=np.uint8)
+    ref = CO.sr_u8(frames, luts, 2, "sdy", 2)
+    with LutEngine(luts, 2, "sdy", 2, 4, device=0, kernel=3) as eng:
+        out = _run(eng, frames)
+    assert (out == ref).all(), (shape, C, int((out != ref).sum()))
+
+
+@pytest.mark.parametrize("orphans", ["1", "0"])
+@pytest.mark.parametrize("kind", ["dark", "bright", "two_level", "ramp", "sparse_bins", "single_bin"])
+def test_binned_skewed_value_distributions(kind, orphans, monkeypatch):
+    """The CTA allocation follows the sample histogram: exercise empty, tiny and
+    dominant bins (single stage, so the engine's input IS the binned stage's input)."""
+    from mulut_b200.infer import LutEngine
+    monkeypatch.setenv("MULUT_BN_ORPHANS", orphans)
+    rng = np.random.default_rng(5)
+    H, W = 150, 240
+    if kind == "dark":
+        img = rng.integers(0, 20, (1, H, W, 3))
+    elif kind == "bright":
+        img = rng.integers(236, 256, (1, H, W, 3))
+    elif kind == "two_level":
+        img = np.where(rng.random((1, H, W, 3)) < 0.5, 3, 250)
+    elif kind == "ramp":
+        img = np.broadcast_to((np.arange(W) * 255 // (W - 1))[None, None, :, None], (1, H, W, 3))
+    elif kind == "sparse_bins":
+        img = rng.integers(96, 160, (1, H, W, 3))
+        img[0, ::37, ::41] = rng.integers(0, 256, img[0, ::37, ::41].shape)
+    else:
+        img = rng.integers(128, 160, (1, H, W, 3))
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    luts = O.random_luts(9, 1, "sdy", 2)
+    ref = CO.sr_u8(img, luts, 1, "sdy", 2)
+    with LutEngine(luts, 1, "sdy", 2, 4, device=0, kernel=3) as eng:
+        out = _run(eng, img)
+    assert (out == ref).all(), (kind, int((out != ref).sum()))
+
+
+@pytest.mark.parametrize("modes,stages", [("s", 1), ("yd", 2), ("dsy", 3)])
+def test_binned_mode_subsets_and_stages(modes, stages, monkeypatch):
+    from mulut_b200.infer import LutEngine
+    monkeypatch.setenv("MULUT_BN_ORPHANS", "0")
+    rng = np.random.default_rng(11)
+    luts = O.random_luts(21, stages, modes, 2)
+    frames = rng.integers(0, 256, (2, 50, 112, 3), dtype=np.uint8)
+    ref = CO.sr_u8(frames, luts, stages, modes, 2)
+    with LutEngine(luts, stages, modes, 2, 4, device=0, kernel=3) as eng:
+        out = _run(eng, frames)
+    assert (out == ref).all(), (modes, stages, int((out != ref).sum()))
+
+
+def test_binned_falls_back_when_tma_cannot_map_the_frame():
+    """W*C % 16 != 0: the forced binned selection runs K1c instead (still bit-exact)."""
+    import torch
+    from mulut_b200.infer import LutEngine
+    rng = np.random.default_rng(3)
+    luts = O.random_luts(4, 2, "sdy", 2)
+    img = rng.integers(0, 256, (41, 37, 3), dtype=np.uint8)
+    with LutEngine(luts, 2, "sdy", 2, 4, device=0, kernel=3) as eng:
+        eng.profile(True)
+        out = eng(torch.from_numpy(img).cuda()).cpu().numpy()
+        prof = eng.profile_read()
+    assert "last_tiled" in prof and "last_binned" not in prof
+    assert (out == CO.sr_u8(img, luts, 2, "sdy", 2)).all()
+
+
+def test_orphan_list_gets_the_sparse_bins():
+    """A frame whose values sit in two bins plus a sprinkle elsewhere: the sprinkle must go
+    through the orphan list kernel, the two dense bins through shared memory."""
+    import torch
+    from mulut_b200.infer import LutEngine
+    rng = np.random.default_rng(12)
+    img = rng.integers(96, 160, (2, 256, 384, 3))
+    sel = rng.random(img.shape) < 0.004
+    img[sel] = rng.integers(0, 256, int(sel.sum()))
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    luts = O.random_luts(13, 1, "sdy", 2)
+    ref = CO.sr_u8(img, luts, 1, "sdy", 2)
+    with LutEngine(luts, 1, "sdy", 2, 4, device=0, kernel=3) as eng:
+        eng.profile(True)
+        out = eng(torch.from_numpy(img).cuda()).cpu().numpy()
+        prof = eng.profile_read()
+    assert "last_binned" in prof and "bin_orphans" in prof, prof
+    assert (out == ref).all(), int((out != ref).sum())
+
+
+def test_auto_picks_binned_for_large_launches_and_host_path_agrees():
+    import torch
+    from mulut_b200.infer import LutEngine
+    rng = np.random.default_rng(8)
+    luts = O.random_luts(2, 2, "sdy", 2)
+    frames = rng.integers(0, 256, (2, 540, 960, 3), dtype=np.uint8)
+    ref = CO.sr_u8(frames, luts, 2, "sdy", 2)
+    with LutEngine(luts, 2, "sdy", 2, 4, device=0) as eng:
+        eng.profile(True)
+        out = eng(torch.from_numpy(frames).cuda()).cpu().numpy()
+        prof = eng.profile_read()
+        assert "last_binned" in prof, prof
+        assert (out == ref).all(), int((out != ref).sum())
+        assert (eng(frames) == ref).all()          # host path: one frame per launch

@@ -10,7 +10,7 @@ from oracle import mulut_oracle as O
 pytestmark = pytest.mark.gpu
 
 NAMES = ["baby", "bird", "butterfly", "head", "woman"]
-KERNELS = {"generic": 0, "tiled": 1, "cell": 2}   # 1 = quad-cooperative K1c, 2 = owner-only K1d
+KERNELS = {"generic": 0, "tiled": 1, "cell": 2, "binned": 3}   # 1 = quad K1c, 2 = owner-only K1d, 3 = binned smem K1f
 
 
 def _engine(luts, stages, modes, scale, kernel="tiled"):
