@@ -132,6 +132,8 @@ static int run_stages(mulut_handle_s *h, Workspace &w, const uint8_t *d_in, uint
             a.modes[m] = h->modes[m];
         }
         a.taps = h->taps;
+        // the explicit TILED selections keep the pre-TMA stage kernel (K1a) as a cross-check of K1g
+        a.no_tma = (h->kernel == MULUT_KERNEL_TILED_QUAD || h->kernel == MULUT_KERNEL_TILED_CELL) ? 1 : 0;
         int done = 1;
         // K1f (binned, shared-memory slabs) when forced, or on AUTO for launches big enough to
         // amortise one 177 KB LUT load per SM; it falls through to K1c when TMA cannot map the frames.

@@ -12,6 +12,7 @@ struct StageArgs {
     int n_modes;
     int interval;
     int last;                                // last stage: up = scale, avg = M, bias 0
+    int no_tma;                              // force the pre-TMA kernels (K1a) for cross-checks
     int num_sms;
     const int8_t *lut[MULUT_MAX_MODES];      // reference layout: int8 (L^4, up^2)
     const uint8_t *lut_alt[MULUT_MAX_MODES]; // device re-layout used by the tiled kernels
@@ -56,6 +57,11 @@ int launch_stage_generic(const StageArgs &a, int up, cudaStream_t stream);
 int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStream_t stream, int *launches,
                           Prof *prof, bool owner_only);
 bool tiled_supported(int up, int interval, int n_modes);
+
+// K1g, the TMA-fed shared-memory kernel for up = 1 stages (infer_stage1.cu); same int16 partial
+// planes as K1a.  Returns MULUT_OK, an error (< 0) or +1 (frames not TMA-mappable: run K1a).
+bool stage1_tma_supported(const StageArgs &a, int up);
+int launch_stage1_tma(const StageArgs &a, int16_t *partial, cudaStream_t stream);
 
 // K1f, the binned shared-memory kernel for the up = 2 last stage (infer_binned.cu).
 // binned_supported: configuration + TMA preconditions (16-byte aligned frames, W*C % 16 == 0).

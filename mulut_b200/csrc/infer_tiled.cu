@@ -852,7 +852,10 @@ int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStre
     if (a.C != 1 && a.C != 2 && a.C != 3 && a.C != 4) return 1;
     if (up == 1) {
         prof->begin(MULUT_PROF_SMEM_STAGE, stream);
-        int rc = a.C == 3 ? launch_smem_stage<3>(a, partial, stream)
+        int rc = 1;
+        if (!a.no_tma && stage1_tma_supported(a, up)) rc = launch_stage1_tma(a, partial, stream);   // K1g
+        if (rc == 1)                                                                                // K1a
+            rc = a.C == 3 ? launch_smem_stage<3>(a, partial, stream)
                : a.C == 1 ? launch_smem_stage<1>(a, partial, stream)
                           : launch_smem_stage<0>(a, partial, stream);
         prof->end(stream);
