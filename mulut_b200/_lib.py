@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmulut_b200.so")
+# MULUT_B200_LIB selects an instrumented side build (tools/bn_timing.py); the product never sets it
+LIB_PATH = os.environ.get("MULUT_B200_LIB") or os.path.join(_HERE, "libmulut_b200.so")
 
 OK, E_BAD_MODE, E_BAD_ARG, E_CUDA, E_NOMEM, E_LUT_SMALL = 0, -1, -2, -3, -4, -5
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED, KERNEL_TILED_QUAD, KERNEL_TILED_CELL, KERNEL_TILED_BINNED = -1, 0, 1, 1, 2, 3

@@ -37,7 +37,20 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), lib_path: str = LIB_PATH) -> str:
+    """defines: extra -D macros (e.g. ["MULUT_BN_TIMING"]) for an instrumented side build; such a
+    build goes to its own object directory and `lib_path`, never over the product library."""
+    global OBJ_DIR
+    obj_dir_saved = OBJ_DIR
+    if defines:
+        OBJ_DIR = os.path.join(obj_dir_saved, "_".join(defines).lower())
+    try:
+        return _build(force, verbose, ["-D" + d for d in defines], lib_path)
+    finally:
+        OBJ_DIR = obj_dir_saved
+
+
+def _build(force: bool, verbose: bool, extra, lib_path: str) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     hdrs = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS] + [os.path.abspath(__file__)]
     objs = []
@@ -50,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [sp] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", obj]
             procs.append((src, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     failed = False
     for src, p in procs:
@@ -60,10 +73,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed (see log above)")
-    if force or procs or _stale(LIB_PATH, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
+    if force or procs or _stale(lib_path, objs):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path] + objs
         subprocess.check_call(cmd, env=env)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -50,7 +50,8 @@ constexpr int BN_SLOT = BN_BOXW * BN_BOXH;      // 4608 B per ring slot, 128-B a
 constexpr int BN_RING = 8;
 constexpr int BN_AHEAD = 3;                     // TMA prefetch distance in tiles
 constexpr int BN_CARRY = BN_RING - BN_AHEAD - 1;   // tiles a queue entry may outlive its scan
-constexpr int BN_THREADS = 768;
+constexpr int BN_THREADS = 768;                 // 24 warps (1024 threads fit at 62 registers but measured no faster)
+constexpr int BN_SCAN_THREADS = 768;            // TW/4 x TH words of a tile, one per scanning thread
 constexpr int BN_QCAP = 8192;                   // queue capacity: power of two > (THREADS - 1 + TW*TH) + TW*TH
 constexpr int BN_SLAB_WORDS = 4916;             // 17^3 = 4913 rows, padded so a slab is a 16-B multiple
 constexpr int BN_SLAB_BYTES = BN_SLAB_WORDS * 4;
@@ -59,7 +60,8 @@ constexpr int BN_MAX_MODES = 3;
 constexpr int BN_BINS = 8;
 constexpr size_t BN_SMEM = (size_t)BN_RING * BN_SLOT + BN_QCAP * 2 + (size_t)BN_MAX_MODES * BN_BIN_BYTES;
 
-static_assert(BN_TW / 4 * BN_TH == BN_THREADS, "scan mapping: one 4-sample word per thread");
+static_assert(BN_TW / 4 * BN_TH == BN_SCAN_THREADS && BN_SCAN_THREADS % 32 == 0 && BN_SCAN_THREADS <= BN_THREADS,
+              "scan mapping: one 4-sample word per scanning thread, whole warps");
 static_assert(BN_QCAP >= BN_THREADS + 2 * BN_TW * BN_TH, "queue too small");
 static_assert(BN_HX + BN_TW + 2 * 4 <= BN_BOXW && 2 * 4 <= BN_HX, "box too narrow for C <= 4");
 
@@ -287,6 +289,21 @@ struct BinnedArgs {
     const BinCtl *ctl;                       // plan: CTAs per bin
 };
 
+// Optional phase timing (build with -DMULUT_BN_TIMING): thread 0 of every CTA accumulates
+// clock64() deltas per phase; read back with mulut_debug_bn_timing().
+#ifdef MULUT_BN_TIMING
+__device__ unsigned long long g_bn_timing[256 * 8];
+#define BN_T0() unsigned long long t_prev = clock64(), t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define BN_T(k) do { if (tid == 0) { const unsigned long long t_now = clock64(); t_acc[k] += t_now - t_prev; t_prev = t_now; } } while (0)
+#define BN_TN(k, n) do { if (tid == 0) t_acc[k] += (n); } while (0)
+#define BN_TEND() do { if (tid == 0) for (int k = 0; k < 8; ++k) g_bn_timing[(blockIdx.x & 255) * 8 + k] = t_acc[k]; } while (0)
+#else
+#define BN_T0() do {} while (0)
+#define BN_T(k) do {} while (0)
+#define BN_TN(k, n) do {} while (0)
+#define BN_TEND() do {} while (0)
+#endif
+
 template <int CT>
 __global__ void __launch_bounds__(BN_THREADS, 1)
 stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_constant__ CUtensorMap tmap)
@@ -365,9 +382,11 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
     // Threads drift by at most one scan: the queue holds a whole tile beyond the unconsumed entries,
     // the two entry counters alternate, and a ring slot is re-filled only after the barrier that
     // follows the rounds that drained it.
+    BN_T0();
     for (int i = 0; i < n_my; ++i) {
         const int slot = i % BN_RING;
         mbar_wait(smem_u32(&s_full[slot]), (uint32_t)(i / BN_RING) & 1u);
+        BN_T(0);
         const int4 info = s_info[slot];
         uint8_t *tile = s_ring + slot * BN_SLOT;
         if (info.w) {
@@ -387,8 +406,9 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
             }
         }
 
-        // ---- scan: queue the samples of my bin (4 samples = one word per thread) ----
-        {
+        BN_T(1);
+        // ---- scan: queue the samples of my bin (4 samples = one word per thread of the first 24 warps) ----
+        if (tid < BN_SCAN_THREADS) {
             const uint32_t w = *reinterpret_cast<const uint32_t *>(tile + scan_off);
             const bool valid = (info.y + srow < a.H) && (info.z + swc * 4 < WC);      // WC % 16 == 0: whole words
             const uint32_t x = ((w >> 5) & 0x07070707u) ^ bin_pat;                    // byte == 0  <=>  sample in my bin
@@ -413,8 +433,10 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
                 ++pos;
             }
         }
+        BN_T(2);
         if (i == 0) mbar_wait(smem_u32(&s_lutbar), 0u);
         __syncthreads();
+        BN_T(3);
         {
             const uint32_t c = *reinterpret_cast<volatile uint32_t *>(&s_cnt[i & 1]);
             if (i & 1) { tail += c - seen1; seen1 = c; } else { tail += c - seen0; seen0 = c; }
@@ -476,8 +498,13 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
                     }
             }
             head += n;
+            BN_TN(5, 1);
+            BN_TN(6, n);
         }
+        BN_T(4);
+        BN_TN(7, 1);
     }
+    BN_TEND();
 }
 
 // ---------------------------------------------------------------------------
@@ -549,3 +576,18 @@ int launch_stage_binned(const StageArgs &a, void *ctl_mem, uint32_t *list, size_
 }
 
 }  // namespace mulut
+
+#ifdef MULUT_BN_TIMING
+// out[8]: mean over CTAs of {wait, fixup, scan, barrier, rounds} cycles, rounds, entries, visits
+extern "C" int mulut_debug_bn_timing(double *out, int n_ctas)
+{
+    static unsigned long long h[256 * 8];
+    if (cudaMemcpyFromSymbol(h, mulut::g_bn_timing, sizeof h) != cudaSuccess) return -1;
+    for (int k = 0; k < 8; ++k) {
+        double acc = 0;
+        for (int b = 0; b < n_ctas && b < 256; ++b) acc += (double)h[b * 8 + k];
+        out[k] = acc / n_ctas;
+    }
+    return 0;
+}
+#endif

@@ -1,10 +1,11 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
-tail -8 gpurun_out/pytest_gpu.log
-for cfg in cfg2 x2s1 cfg3; do
+timeout 900 python -m pytest tests/test_gpu_binned.py -x -q -m gpu > gpurun_out/pytest_binned.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/pytest_binned.log
+python tools/bn_timing.py --config cfg2
+python tools/bn_timing.py --config x2s1
+for cfg in cfg2 x2s1; do
 timeout 300 python bench.py --config $cfg --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_auto_${cfg}.json 2> gpurun_out/bench_auto.err; echo "bench rc=$?"
-tail -3 gpurun_out/bench_auto.err
 python - <<PY
 import json
 d=json.load(open('gpurun_out/bench_auto_${cfg}.json'))
