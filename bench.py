@@ -141,7 +141,7 @@ def gather_peak(device):
     out = (ctypes.c_double * 3)()
     res = {}
     for name, table, bps, tpb in [("quad_cell64", 12 << 20, 4, 512), ("ldg_u32", 1 << 20, 4, 512),
-                                  ("lds_u8", 83584, 2, 512)]:
+                                  ("lds_u8", 83584, 2, 512), ("lds_u32", 176976, 1, 768)]:
         rc = L.mulut_gather_bench(device, _lib.GB_VARIANTS[name], table, 256, bps, tpb, 3, out)
         if rc == 0:
             res[name] = {"gathers_per_s": out[0], "useful_GBps": out[1] / 1e9}
@@ -301,40 +301,72 @@ def main():
         return
 
     # ---------------- roofline of the dominant kernel ----------------
+    # Per kernel kind: vertex gathers per input sample, LUT bytes per gather (algorithmic), algorithmic HBM
+    # bytes per sample, and which measured gather primitive is its ceiling.
+    r2, M = SCALE * SCALE, len(MODES)
+    KINFO = {
+        "smem_stage":    (60, 1, 1 + 2 * M, "lds_u8", "K1g/K1a: 1-byte vertex gathers from the shared-memory LUT"),
+        "generic_stage": (60, 1, 2, "ldg_u32", "K0: vertex gathers through L1/L2"),
+        "last_binned":   (60, r2, 1 + r2, "lds_u32", "K1f: 4-byte vertex-row gathers from shared-memory LUT slabs"),
+        "last_tiled":    (60, r2, 1 + r2, "quad_cell64", "K1c/K1e: 64-byte cell fetches from L1/L2 (one per 5 vertices)"),
+        "generic_last":  (60, r2, 1 + r2, "ldg_u32", "K0: vertex gathers through L1/L2"),
+        "combine":       (0, 0, 2 * M + 1, None, "K1b: streaming"),
+        "bin_hist":      (0, 0, 2, None, "K1f preparation: streaming"),
+        "bin_orphans":   (0, 0, 0, None, "K1f orphan list"),
+    }
     samples_per_step = F * H * W * C
     hbm_peak, peak_src = measured_peaks()
     dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, (0.0, 0))
     dom_name, (dom_ms, dom_n) = dom
-    gather_b = {"last_tiled": GATHER_B_STAGE2, "last_binned": GATHER_B_STAGE2, "generic_last": GATHER_B_STAGE2, "smem_stage": GATHER_B_STAGE1,
-                "generic_stage": GATHER_B_STAGE1, "combine": 0}.get(dom_name, 0)
-    hbm_b = {"last_tiled": 1 + SCALE * SCALE, "last_binned": 1 + SCALE * SCALE, "generic_last": 1 + SCALE * SCALE, "smem_stage": 1 + 2 * len(MODES),
-             "generic_stage": 2, "combine": 2 * len(MODES) + 1}.get(dom_name, HBM_B)
+    n_gather, b_gather, hbm_b, peak_variant, kdesc = KINFO.get(dom_name, (0, 0, HBM_B, None, ""))
     per_launch_s = dom_ms * 1e-3 / max(dom_n, 1)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tp):
         try:
-            traffic = json.load(open(tp)).get(dom_name)
+            t = json.load(open(tp)).get(dom_name)
+            if t is not None:      # measured DRAM bytes per input sample (ncu --set full), scaled to this launch
+                traffic = t["dram_bytes_per_sample"] * samples_per_step
         except Exception:
             traffic = None
     ach_hbm = samples_per_step * hbm_b / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": ach_hbm, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach_hbm / hbm_peak, "traffic": traffic, "peak_source": peak_src + " (of measured)",
+                "frac": ach_hbm / hbm_peak, "traffic": traffic, "peak_source": peak_src + " (burst copy figure)",
                 "alg_bytes_per_sample": hbm_b, "launch_ms": per_launch_s * 1e3,
                 "share_of_step": dom_ms / ms if ms > 0 else None,
-                "note": "path is cache-gather bound, not HBM bound: see gather_roofline"}
+                "note": "the path is gather/ALU bound on chip, not HBM bound (5 B of HBM per 300 B gathered): "
+                        "see gather_roofline"}
     gp = gather_peak(local)
-    ach_gather = samples_per_step * gather_b / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
-    # denominator: cells/s of the best L2 cell-fetch shape x the 20 B (5 vertices x 4 B) an interpolation needs
-    cell_rate = gp.get("quad_cell64", {}).get("gathers_per_s", 0.0)
+
+    def peak_gathers(variant):
+        g = gp.get(variant, {}).get("gathers_per_s")
+        if not g:
+            return None
+        return g * 5 if variant == "quad_cell64" else g      # one 64-B cell serves the 5 vertices of an interpolation
+
+    ach_gathers = samples_per_step * n_gather / per_launch_s if per_launch_s > 0 else 0.0
+    pk = peak_gathers(peak_variant) if peak_variant else None
+    per_kernel = {}
+    for kname, (kms, kn) in prof.items():
+        ng, bg, _, pv, _ = KINFO.get(kname, (0, 0, 0, None, ""))
+        if not ng or not kn:
+            continue
+        g = samples_per_step * ng / (kms * 1e-3 / kn)
+        kp = peak_gathers(pv)
+        per_kernel[kname] = {"Ggathers_per_s": g / 1e9, "GBps": g * bg / 1e9, "peak_primitive": pv,
+                             "frac": g / kp if kp else None}
     gather_roofline = {
-        "bound": "l2_gather", "kernel": dom_name, "achieved": ach_gather, "unit": "GB/s",
-        "alg_gather_bytes_per_sample": gather_b,
-        "peak": cell_rate * 20 / 1e9 if cell_rate else None,
-        "peak_def": "measured random 64-B cell fetches/s from an L2-resident 12 MB table (4 lanes x LDG.128) x 20 "
-                    "algorithmic bytes (5 vertices x 4 B) per fetch",
-        "frac": (ach_gather / (cell_rate * 20 / 1e9)) if cell_rate else None,
-        "whole_step_achieved": samples_per_step * (GATHER_B_STAGE1 + GATHER_B_STAGE2) * args.steps / (ms * 1e-3) / 1e9,
+        "bound": "on-chip gather (shared memory / L1-L2)", "kernel": dom_name, "kernel_desc": kdesc,
+        "achieved": ach_gathers * b_gather / 1e9, "unit": "GB/s",
+        "achieved_Ggathers_per_s": ach_gathers / 1e9,
+        "alg_gathers_per_sample": n_gather, "alg_bytes_per_gather": b_gather,
+        "peak": pk * b_gather / 1e9 if pk else None,
+        "peak_Ggathers_per_s": pk / 1e9 if pk else None,
+        "peak_def": "micro-benchmark '{}' measured live (mulut_gather_bench): independent random gathers of the same "
+                    "shape from a table of the same kind, all SMs".format(peak_variant),
+        "frac": ach_gathers / pk if pk else None,
+        "whole_step_Ggathers_per_s": samples_per_step * 120 * args.steps / (ms * 1e-3) / 1e9 if STAGES == 2 else None,
+        "per_kernel": per_kernel,
         "microbench": gp,
     }
     kernels = {k: {"ms_total": v[0], "launches": v[1], "ms_per_launch": v[0] / v[1]} for k, v in prof.items()}

@@ -144,8 +144,8 @@ bin_hist_kernel(const uint8_t *__restrict__ img, size_t total, BinCtl *__restric
 // A bin is worth a resident CTA group only if its samples outweigh the fixed cost of
 // walking every tile once more (scan + barriers); sparse bins go to a list that the
 // generic L2-gather kernel finishes (stage_generic_list_kernel).  Costs in SM cycles.
-constexpr unsigned long long BN_CV = 1000;      // per tile visit of one CTA
-constexpr unsigned long long BN_CS = 8;         // per sample interpolated from shared memory
+constexpr unsigned long long BN_CV = 1200;      // per tile visit of one CTA (tools/bn_timing.py: 1140-1200)
+constexpr unsigned long long BN_CS = 11;        // per sample interpolated from shared memory (measured 10.7-14.4)
 constexpr unsigned long long BN_CG = 26;        // per sample interpolated by the list kernel
 __global__ void bin_plan_kernel(BinCtl *__restrict__ ctl, long long n_tiles, int G, unsigned long long list_cap,
                                 int allow_orphans)
