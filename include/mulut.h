@@ -139,6 +139,30 @@ int mulut_interp_bwd_f32(const float *d_weight, int n_rows, int up, char mode,
                          int interval, const float *d_grad_out,
                          float *d_grad_weight, float *d_grad_img_in, void *stream);
 
+/*
+ * K4: one whole stage of MuLUT.forward, sr/model.py:296-310, fused: for every mode (in the
+ * order of `modes`) and rotation 0..3
+ *     pred = round(pred + rot90_back(InterpTorchBatch(weight_mode, up, mode, pad(rot90(x, r)))))
+ * then  x' = round(clamp(pred / avg + bias, 0, 255))  - no rotated or padded copies are made.
+ *   d_weights  n_modes raw parameter tables, float32 (n_rows, up^2) each
+ *   d_x        float32 (B, C, h, w), integer-valued 0..255 (the reference's x * 255)
+ *   d_out      float32 (B, C, h*up, w*up) = x'
+ *   d_mask     uint8, same shape: 1 where 0 <= pred/avg + bias <= 255 (clamp passes the gradient)
+ */
+int mulut_stage_fwd_f32(const float *const *d_weights, int n_modes, const char *modes, int n_rows,
+                        int up, int interval, const float *d_x, int B, int C, int h, int w,
+                        float avg, float bias, float *d_out, uint8_t *d_mask, void *stream);
+/*
+ * Backward of the fused stage (what autograd derives for model.py:296-310 with BPDA rounding,
+ * model.py:59-67): G_pred = grad_out * mask / avg feeds all 4*n_modes passes.
+ *   d_grad_weights  n_modes tables float32 (n_rows, up^2), ACCUMULATED INTO; entries may be NULL
+ *   d_grad_x        float32 (B, C, h, w), ACCUMULATED INTO; may be NULL
+ */
+int mulut_stage_bwd_f32(const float *const *d_weights, int n_modes, const char *modes, int n_rows,
+                        int up, int interval, const float *d_x, int B, int C, int h, int w,
+                        float avg, float bias, const float *d_grad_out, const uint8_t *d_mask,
+                        float *const *d_grad_weights, float *d_grad_x, void *stream);
+
 /* Pinned host memory for the *_host entry points. */
 void *mulut_host_alloc(size_t bytes);
 int mulut_host_free(void *p);

@@ -255,6 +255,259 @@ interp_pass_f64_kernel(const __grid_constant__ F32Args a, int rot, double *__res
     }
 }
 
+// ===========================================================================
+// K4: one whole stage of MuLUT.forward (sr/model.py:296-310) in ONE kernel per
+// direction.  The reference runs, per stage, 12 x { rot90 -> replicate-pad ->
+// InterpTorchBatch -> rot90 back -> pred += -> round_func }.  Here every input pixel
+// walks its 12 (mode, rotation) interpolations with rotated tap offsets and clamped
+// coordinates (no image is rotated or padded), accumulating pred in registers with
+// the reference's rounding after every pass, then applies
+// x' = round(clamp(pred / avg + bias, 0, 255)) and records the clamp mask.
+// The backward kernel mirrors it (all round_func are identity, BPDA model.py:59-67):
+// G_pred = G * mask / avg feeds all 12 passes; LUT gradients leave through vector
+// red.global.add, input gradients are accumulated per tile in shared memory first.
+// ===========================================================================
+struct StageF32Args {
+    const float *x;                          // (BC, h, w), integer-valued 0..255
+    int BC, h, w, n_modes, interval, n_rows;
+    float avg, bias;
+    const float *weight[MULUT_MAX_MODES];    // raw parameters (n_rows, up^2)
+    float *gweight[MULUT_MAX_MODES];         // backward only: accumulated into
+    TapTable taps;
+};
+
+// simplex of four tap VALUES (model.py:122-160 without the pad/rotate bookkeeping)
+__device__ __forceinline__ void simplex_from_taps(const float (&t)[4], int interval, int n_rows, Simplex &s)
+{
+    const float q = (float)(1 << interval);
+    const int L = (1 << (8 - interval)) + 1;
+    const int stride[4] = {L * L * L, L * L, L, 1};
+    float f[4];
+    int v0 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int m;
+        split_msb_lsb(t[k], q, m, f[k]);
+        v0 += m * stride[k];
+    }
+    sort_taps(f, s.order);
+    float fs[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        fs[p] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (s.order[p] == k) fs[p] = f[k];
+    }
+    s.v[0] = v0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        int st = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (s.order[p] == k) st = stride[k];
+        s.v[p + 1] = s.v[p] + st;
+    }
+#pragma unroll
+    for (int p = 0; p < 5; ++p) s.v[p] = min(max(s.v[p], 0), n_rows - 1);   // memory safety only
+    s.w[0] = q - fs[0];
+    s.w[1] = fs[0] - fs[1];
+    s.w[2] = fs[1] - fs[2];
+    s.w[3] = fs[2] - fs[3];
+    s.w[4] = fs[3];
+}
+
+template <int UP>
+__global__ void __launch_bounds__(256)
+stage_fwd_kernel(const __grid_constant__ StageF32Args a, float *__restrict__ out, uint8_t *__restrict__ mask)
+{
+    constexpr int UP2 = UP * UP;
+    const size_t total = (size_t)a.BC * a.h * a.w;
+    const float inv_q = 1.f / (float)(1 << a.interval);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % a.w);
+        const size_t rr = i / a.w;
+        const int y = (int)(rr % a.h);
+        const size_t bc = rr / a.h;
+        const float *__restrict__ plane = a.x + bc * (size_t)a.h * a.w;
+        float pred[UP2];
+#pragma unroll
+        for (int j = 0; j < UP2; ++j) pred[j] = 0.f;
+        for (int m = 0; m < a.n_modes; ++m) {
+            const float *__restrict__ W = a.weight[m];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float t[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int yy = clampi(y + a.taps.dy[m][r][k], 0, a.h - 1);
+                    const int xx = clampi(x + a.taps.dx[m][r][k], 0, a.w - 1);
+                    t[k] = __ldg(plane + (size_t)yy * a.w + xx);
+                }
+                Simplex s;
+                simplex_from_taps(t, a.interval, a.n_rows, s);
+                float o[UP2];
+#pragma unroll
+                for (int j = 0; j < UP2; ++j) o[j] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const float *__restrict__ row = W + (size_t)s.v[k] * UP2;
+#pragma unroll
+                    for (int j = 0; j < UP2; ++j) o[j] = __fadd_rn(o[j], __fmul_rn(s.w[k], quant(__ldg(row + j))));
+                }
+                // pred += rot_back(o / q); pred = round(pred)   (model.py:306-308, half-to-even)
+#pragma unroll
+                for (int j = 0; j < UP2; ++j) {
+                    const int p = subpixel_perm<UP>(r, j);
+                    pred[p] = rintf(__fadd_rn(pred[p], __fmul_rn(o[j], inv_q)));
+                }
+            }
+        }
+        // x = round(clamp(pred / avg + bias, 0, 255))   (model.py:309)
+#pragma unroll
+        for (int u = 0; u < UP; ++u)
+#pragma unroll
+            for (int v = 0; v < UP; ++v) {
+                const float pre = __fadd_rn(__fdiv_rn(pred[u * UP + v], a.avg), a.bias);
+                const size_t o_idx = (bc * a.h * UP + (size_t)y * UP + u) * ((size_t)a.w * UP) + (size_t)x * UP + v;
+                out[o_idx] = rintf(fminf(fmaxf(pre, 0.f), 255.f));
+                mask[o_idx] = (pre >= 0.f && pre <= 255.f) ? 1 : 0;
+            }
+    }
+}
+
+constexpr int K4_T = 16;                 // backward tile: 16 x 16 input pixels per CTA
+constexpr int K4_P = K4_T + 4;           // + 2-pixel halo on every side
+
+template <int UP>
+__global__ void __launch_bounds__(K4_T * K4_T)
+stage_bwd_kernel(const __grid_constant__ StageF32Args a, const float *__restrict__ gout,
+                 const uint8_t *__restrict__ mask, float *__restrict__ gx)
+{
+    constexpr int UP2 = UP * UP;
+    __shared__ float s_gx[K4_P * K4_P];
+    const int tiles_x = (a.w + K4_T - 1) / K4_T, tiles_y = (a.h + K4_T - 1) / K4_T;
+    const int tx = blockIdx.x % tiles_x;
+    const int ty = (blockIdx.x / tiles_x) % tiles_y;
+    const size_t bc = blockIdx.x / (tiles_x * tiles_y);
+    const int lx = threadIdx.x % K4_T, ly = threadIdx.x / K4_T;
+    const int x = tx * K4_T + lx, y = ty * K4_T + ly;
+    const float inv_q = 1.f / (float)(1 << a.interval);
+    for (int i = threadIdx.x; i < K4_P * K4_P; i += blockDim.x) s_gx[i] = 0.f;
+    __syncthreads();
+
+    if (x < a.w && y < a.h) {
+        const float *__restrict__ plane = a.x + bc * (size_t)a.h * a.w;
+        // g = dL/d(o)  = G * mask / avg / q   (o enters pred as o/q; the rounds are identity)
+        float g[UP2];
+#pragma unroll
+        for (int u = 0; u < UP; ++u)
+#pragma unroll
+            for (int v = 0; v < UP; ++v) {
+                const size_t o_idx = (bc * a.h * UP + (size_t)y * UP + u) * ((size_t)a.w * UP) + (size_t)x * UP + v;
+                g[u * UP + v] = mask[o_idx] ? __fdiv_rn(__ldg(gout + o_idx), a.avg) * inv_q : 0.f;
+            }
+        for (int m = 0; m < a.n_modes; ++m) {
+            const float *__restrict__ W = a.weight[m];
+            float *__restrict__ GW = a.gweight[m];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float t[4];
+                int sidx[4];                                  // tile-local index of each tap (clamped coordinate)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int yy = clampi(y + a.taps.dy[m][r][k], 0, a.h - 1);
+                    const int xx = clampi(x + a.taps.dx[m][r][k], 0, a.w - 1);
+                    t[k] = __ldg(plane + (size_t)yy * a.w + xx);
+                    sidx[k] = (yy - ty * K4_T + 2) * K4_P + (xx - tx * K4_T + 2);
+                }
+                Simplex s;
+                simplex_from_taps(t, a.interval, a.n_rows, s);
+                float gr[UP2];                                // this rotation's view of g: column j <- sub-pixel perm(r, j)
+#pragma unroll
+                for (int j = 0; j < UP2; ++j) gr[j] = g[subpixel_perm<UP>(r, j)];
+                float dot_prev = 0.f;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const float *__restrict__ row = W + (size_t)s.v[k] * UP2;
+                    float wraw[UP2];
+#pragma unroll
+                    for (int j = 0; j < UP2; ++j) wraw[j] = __ldg(row + j);
+                    float dot = 0.f;
+#pragma unroll
+                    for (int j = 0; j < UP2; ++j) dot += gr[j] * quant(wraw[j]);
+                    if (GW) {
+                        float *__restrict__ gw = GW + (size_t)s.v[k] * UP2;
+                        if constexpr (UP2 % 4 == 0) {
+#pragma unroll
+                            for (int j = 0; j < UP2; j += 4) {
+                                float c[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    c[e] = quant_pass(wraw[j + e]) ? 127.f * (s.w[k] * gr[j + e]) : 0.f;
+                                red_add_v4(gw + j, c[0], c[1], c[2], c[3]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < UP2; ++j)
+                                if (quant_pass(wraw[j])) atomicAdd(gw + j, 127.f * (s.w[k] * gr[j]));
+                        }
+                    }
+                    if (gx && k > 0) {
+                        int si = 0;
+#pragma unroll
+                        for (int tt = 0; tt < 4; ++tt)
+                            if (s.order[k - 1] == tt) si = sidx[tt];
+                        atomicAdd(&s_gx[si], dot - dot_prev);
+                    }
+                    dot_prev = dot;
+                }
+            }
+        }
+    }
+    if (gx) {
+        __syncthreads();
+        float *__restrict__ gplane = gx + bc * (size_t)a.h * a.w;
+        for (int i = threadIdx.x; i < K4_P * K4_P; i += blockDim.x) {
+            const int yy = ty * K4_T - 2 + i / K4_P, xx = tx * K4_T - 2 + i % K4_P;
+            const float v = s_gx[i];
+            if (v != 0.f && yy >= 0 && yy < a.h && xx >= 0 && xx < a.w) atomicAdd(gplane + (size_t)yy * a.w + xx, v);
+        }
+    }
+}
+
+static int fill_stage_args(StageF32Args &a, const float *const *weights, int n_modes, const char *modes, int n_rows,
+                           int up, int interval, const float *x, int B, int C, int h, int w, float avg, float bias)
+{
+    if (!weights || !modes || !x || n_modes < 1 || n_modes > MULUT_MAX_MODES || B < 0 || C < 0 || h < 0 || w < 0 ||
+        interval < 1 || interval > 7 || !(avg > 0.f)) {
+        set_error("stage: bad argument");
+        return MULUT_E_BAD_ARG;
+    }
+    if (up < 1 || up > 4) { set_error("stage: upscale %d not supported (1..4)", up); return MULUT_E_BAD_ARG; }
+    memset(&a, 0, sizeof a);
+    if (!build_tap_table(modes, n_modes, &a.taps)) {
+        for (int m = 0; m < n_modes; ++m) {
+            int dy[4], dx[4];
+            if (!mode_taps(modes[m], dy, dx)) { set_error("Mode %c not implemented.", modes[m]); break; }
+        }
+        return MULUT_E_BAD_MODE;
+    }
+    const int L = (1 << (8 - interval)) + 1;
+    if ((long long)n_rows < (long long)L * L * L * L) {
+        set_error("LUT too small: need %lld rows, have %d", (long long)L * L * L * L, n_rows);
+        return MULUT_E_LUT_SMALL;
+    }
+    for (int m = 0; m < n_modes; ++m) {
+        if (!weights[m]) { set_error("stage: weights[%d] is null", m); return MULUT_E_BAD_ARG; }
+        a.weight[m] = weights[m];
+    }
+    a.x = x; a.BC = B * C; a.h = h; a.w = w; a.n_modes = n_modes; a.interval = interval; a.n_rows = n_rows;
+    a.avg = avg; a.bias = bias;
+    return MULUT_OK;
+}
+
 static int fill_args(F32Args &a, const float *weight, int n_rows, int up, char mode, const float *img, int BC,
                      int h, int w, int bd, int interval)
 {
@@ -349,6 +602,60 @@ extern "C" int mulut_interp_pass_f64(const float *d_weight, int n_rows, const fl
     case 2: interp_pass_f64_kernel<2><<<grid_for(total), 256, 0, st>>>(a, rot, d_out); break;
     case 3: interp_pass_f64_kernel<3><<<grid_for(total), 256, 0, st>>>(a, rot, d_out); break;
     default: interp_pass_f64_kernel<4><<<grid_for(total), 256, 0, st>>>(a, rot, d_out); break;
+    }
+    MULUT_CUDA(cudaGetLastError());
+    return MULUT_OK;
+}
+
+extern "C" int mulut_stage_fwd_f32(const float *const *d_weights, int n_modes, const char *modes, int n_rows, int up,
+                                   int interval, const float *d_x, int B, int C, int h, int w, float avg, float bias,
+                                   float *d_out, uint8_t *d_mask, void *stream)
+{
+    StageF32Args a;
+    int rc = fill_stage_args(a, d_weights, n_modes, modes, n_rows, up, interval, d_x, B, C, h, w, avg, bias);
+    if (rc) return rc;
+    if (!d_out || !d_mask) { set_error("stage_fwd: null output"); return MULUT_E_BAD_ARG; }
+    const size_t total = (size_t)B * C * h * w;
+    if (total == 0) return MULUT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (up) {
+    case 1: stage_fwd_kernel<1><<<grid_for(total), 256, 0, st>>>(a, d_out, d_mask); break;
+    case 2: stage_fwd_kernel<2><<<grid_for(total), 256, 0, st>>>(a, d_out, d_mask); break;
+    case 3: stage_fwd_kernel<3><<<grid_for(total), 256, 0, st>>>(a, d_out, d_mask); break;
+    default: stage_fwd_kernel<4><<<grid_for(total), 256, 0, st>>>(a, d_out, d_mask); break;
+    }
+    MULUT_CUDA(cudaGetLastError());
+    return MULUT_OK;
+}
+
+extern "C" int mulut_stage_bwd_f32(const float *const *d_weights, int n_modes, const char *modes, int n_rows, int up,
+                                   int interval, const float *d_x, int B, int C, int h, int w, float avg, float bias,
+                                   const float *d_grad_out, const uint8_t *d_mask, float *const *d_grad_weights,
+                                   float *d_grad_x, void *stream)
+{
+    StageF32Args a;
+    int rc = fill_stage_args(a, d_weights, n_modes, modes, n_rows, up, interval, d_x, B, C, h, w, avg, bias);
+    if (rc) return rc;
+    if (!d_grad_out || !d_mask) { set_error("stage_bwd: null grad_out / mask"); return MULUT_E_BAD_ARG; }
+    bool any = d_grad_x != nullptr;
+    for (int m = 0; m < n_modes; ++m) {
+        a.gweight[m] = d_grad_weights ? d_grad_weights[m] : nullptr;
+        any |= a.gweight[m] != nullptr;
+        if ((up == 2 || up == 4) && (reinterpret_cast<uintptr_t>(a.gweight[m]) & 15)) {
+            set_error("stage_bwd: grad_weights must be 16-byte aligned (vector red.global.add)");
+            return MULUT_E_BAD_ARG;
+        }
+    }
+    const size_t total = (size_t)B * C * h * w;
+    if (total == 0 || !any) return MULUT_OK;
+    const size_t blocks = (size_t)B * C * ((h + K4_T - 1) / K4_T) * ((w + K4_T - 1) / K4_T);
+    if (blocks > 0x7fffffffull) { set_error("stage_bwd: too many tiles"); return MULUT_E_BAD_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (up) {
+    case 1: stage_bwd_kernel<1><<<(unsigned)blocks, K4_T * K4_T, 0, st>>>(a, d_grad_out, d_mask, d_grad_x); break;
+    case 2: stage_bwd_kernel<2><<<(unsigned)blocks, K4_T * K4_T, 0, st>>>(a, d_grad_out, d_mask, d_grad_x); break;
+    case 3: stage_bwd_kernel<3><<<(unsigned)blocks, K4_T * K4_T, 0, st>>>(a, d_grad_out, d_mask, d_grad_x); break;
+    default: stage_bwd_kernel<4><<<(unsigned)blocks, K4_T * K4_T, 0, st>>>(a, d_grad_out, d_mask, d_grad_x); break;
     }
     MULUT_CUDA(cudaGetLastError());
     return MULUT_OK;

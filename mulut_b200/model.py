@@ -59,6 +59,58 @@ class _InterpFunction(torch.autograd.Function):
         return gw, gx, None, None, None, None
 
 
+class _StageFunction(torch.autograd.Function):
+    """K4: one whole stage of MuLUT.forward (model.py:296-310) - 4*len(modes) interpolation
+    passes with their per-pass rounding, the average, bias, clamp and final rounding - as
+    ONE kernel per direction (mulut_stage_fwd_f32 / mulut_stage_bwd_f32)."""
+
+    @staticmethod
+    def forward(ctx, x, upscale, modes, avg, bias, interval, *weights):
+        if not (x.is_cuda and all(w.is_cuda for w in weights)):
+            raise RuntimeError("mulut_b200 fused stage needs CUDA tensors (no CPU fallback)")
+        xs = x.detach().contiguous().float()
+        ws = [w.detach().contiguous().float() for w in weights]
+        B, C, h, wd = xs.shape
+        out = torch.empty((B, C, h * upscale, wd * upscale), dtype=torch.float32, device=xs.device)
+        mask = torch.empty(out.shape, dtype=torch.uint8, device=xs.device)
+        ptrs = (ctypes.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
+        stream = ctypes.c_void_p(torch.cuda.current_stream(xs.device).cuda_stream)
+        with torch.cuda.device(xs.device):
+            _lib.check(_lib.lib().mulut_stage_fwd_f32(ptrs, len(ws), modes.encode(), ws[0].shape[0], upscale, interval,
+                                                      xs.data_ptr(), B, C, h, wd, float(avg), float(bias),
+                                                      out.data_ptr(), mask.data_ptr(), stream))
+        ctx.save_for_backward(xs, mask, *ws)
+        ctx.cfg = (upscale, modes, float(avg), float(bias), interval)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xs, mask, *ws = ctx.saved_tensors
+        upscale, modes, avg, bias, interval = ctx.cfg
+        B, C, h, wd = xs.shape
+        g = grad_out.contiguous().float()
+        gx = torch.zeros_like(xs) if ctx.needs_input_grad[0] else None
+        gws = [torch.zeros_like(w) if ctx.needs_input_grad[6 + i] else None for i, w in enumerate(ws)]
+        ptrs = (ctypes.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
+        gptrs = (ctypes.c_void_p * len(ws))(*[(t.data_ptr() if t is not None else None) for t in gws])
+        stream = ctypes.c_void_p(torch.cuda.current_stream(xs.device).cuda_stream)
+        with torch.cuda.device(xs.device):
+            _lib.check(_lib.lib().mulut_stage_bwd_f32(ptrs, len(ws), modes.encode(), ws[0].shape[0], upscale, interval,
+                                                      xs.data_ptr(), B, C, h, wd, avg, bias, g.data_ptr(),
+                                                      mask.data_ptr(), gptrs,
+                                                      gx.data_ptr() if gx is not None else None, stream))
+        return (gx, None, None, None, None, None) + tuple(gws)
+
+
+def fused_stage(x, weights, upscale, modes, avg, bias, interval=4):
+    """x' = round(clamp(sum-with-per-pass-rounding / avg + bias, 0, 255)) for one stage."""
+    modes = "".join(modes)
+    for m in modes:
+        if m not in ("s", "d", "y"):
+            raise ValueError("Mode {} not implemented.".format(m))
+    return _StageFunction.apply(x, int(upscale), modes, float(avg), float(bias), int(interval), *weights)
+
+
 def interp_torch_batch(weight, upscale, mode, img_in, bd, interval=4):
     if mode not in ("s", "d", "y"):
         raise ValueError("Mode {} not implemented.".format(mode))      # model.py:119-121
@@ -68,8 +120,11 @@ def interp_torch_batch(weight, upscale, mode, img_in, bd, interval=4):
 class MuLUT(nn.Module):
     """PyTorch version of MuLUT for LUT-aware fine-tuning (kernel-backed)."""
 
-    def __init__(self, lut_folder, stages, modes, upscale=4, interval=4, luts=None):
+    def __init__(self, lut_folder, stages, modes, upscale=4, interval=4, luts=None, fused=True):
         super().__init__()
+        # fused=True: every stage is one K4 kernel per direction; fused=False keeps the reference's
+        # loop of 4*len(modes) InterpTorchBatch calls per stage (each a K2/K3 kernel) - same results
+        self.fused = fused
         self.interval = interval
         self.upscale = upscale
         self.modes = modes
@@ -107,6 +162,13 @@ class MuLUT(nn.Module):
             else:
                 avg_factor, bias = len(modes) * 4, 127
                 scale = 1
+            if self.fused:
+                for mode in modes:
+                    if mode not in ("s", "d", "y"):
+                        raise ValueError("Mode {} not implemented.".format(mode))
+                weights = [getattr(self, "weight_s{}_{}".format(stage, mode)) for mode in modes]
+                x = fused_stage(x, weights, scale, modes, avg_factor, bias, self.interval)
+                continue
             for mode in modes:
                 pad = mode_pad_dict[mode]
                 weight = getattr(self, "weight_s{}_{}".format(stage, mode))

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--aten", action="store_true")
+    ap.add_argument("--loop", action="store_true", help="reference-style loop of 24 InterpTorchBatch calls (K2/K3) instead of the fused stages (K4)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -49,7 +50,7 @@ def main():
 
     dev = torch.device("cuda", local)
     luts = shipped_luts()
-    net = MuLUT(None, 2, ["s", "d", "y"], upscale=4, interval=4, luts=luts).to(dev)
+    net = MuLUT(None, 2, ["s", "d", "y"], upscale=4, interval=4, luts=luts, fused=not args.loop).to(dev)
     params = list(net.parameters())
     bucket = FlatGradBucket(params)
     opt = torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
