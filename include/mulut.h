@@ -148,10 +148,15 @@ int mulut_interp_bwd_f32(const float *d_weight, int n_rows, int up, char mode,
  *   d_x        float32 (B, C, h, w), integer-valued 0..255 (the reference's x * 255)
  *   d_out      float32 (B, C, h*up, w*up) = x'
  *   d_mask     uint8, same shape: 1 where 0 <= pred/avg + bias <= 255 (clamp passes the gradient)
+ *   d_workspace  mulut_stage_workspace_bytes() bytes, 16-byte aligned, caller-owned: the forward
+ *              writes the quantised tables clamp(round(w*127), -127, 127) (model.py:74-76) there as
+ *              int8 rows + clamp flags; hand the SAME buffer to the matching backward call.
  */
+size_t mulut_stage_workspace_bytes(int n_modes, int n_rows, int up);
 int mulut_stage_fwd_f32(const float *const *d_weights, int n_modes, const char *modes, int n_rows,
                         int up, int interval, const float *d_x, int B, int C, int h, int w,
-                        float avg, float bias, float *d_out, uint8_t *d_mask, void *stream);
+                        float avg, float bias, float *d_out, uint8_t *d_mask, void *d_workspace,
+                        void *stream);
 /*
  * Backward of the fused stage (what autograd derives for model.py:296-310 with BPDA rounding,
  * model.py:59-67): G_pred = grad_out * mask / avg feeds all 4*n_modes passes.
@@ -161,7 +166,8 @@ int mulut_stage_fwd_f32(const float *const *d_weights, int n_modes, const char *
 int mulut_stage_bwd_f32(const float *const *d_weights, int n_modes, const char *modes, int n_rows,
                         int up, int interval, const float *d_x, int B, int C, int h, int w,
                         float avg, float bias, const float *d_grad_out, const uint8_t *d_mask,
-                        float *const *d_grad_weights, float *d_grad_x, void *stream);
+                        const void *d_workspace, float *const *d_grad_weights, float *d_grad_x,
+                        void *stream);
 
 /* Pinned host memory for the *_host entry points. */
 void *mulut_host_alloc(size_t bytes);

@@ -47,12 +47,14 @@ SYMBOLS = {
     "mulut_interp_bwd_f32": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_char, _c.c_void_p, _c.c_int, _c.c_int,
                                         _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                         _c.c_void_p, _c.c_void_p]),
+    "mulut_stage_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int]),
     "mulut_stage_fwd_f32": (_c.c_int, [_c.POINTER(_c.c_void_p), _c.c_int, _c.c_char_p, _c.c_int, _c.c_int, _c.c_int,
                                        _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_float,
-                                       _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+                                       _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "mulut_stage_bwd_f32": (_c.c_int, [_c.POINTER(_c.c_void_p), _c.c_int, _c.c_char_p, _c.c_int, _c.c_int, _c.c_int,
                                        _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_float,
-                                       _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p), _c.c_void_p, _c.c_void_p]),
+                                       _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p), _c.c_void_p,
+                                       _c.c_void_p]),
     "mulut_host_alloc": (_c.c_void_p, [_c.c_size_t]),
     "mulut_host_free": (_c.c_int, [_c.c_void_p]),
     "mulut_gather_bench": (_c.c_int, [_c.c_int, _c.c_int, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_int,

@@ -272,9 +272,62 @@ struct StageF32Args {
     int BC, h, w, n_modes, interval, n_rows;
     float avg, bias;
     const float *weight[MULUT_MAX_MODES];    // raw parameters (n_rows, up^2)
+    const int8_t *wq[MULUT_MAX_MODES];       // quantised once per call: clamp(rint(w*127), +-127), rows of q_pitch(up) bytes
+    const uint16_t *wflag[MULUT_MAX_MODES];  // bit j: the clamp passes the gradient of column j (|rint(w*127)| <= 127)
     float *gweight[MULUT_MAX_MODES];         // backward only: accumulated into
     TapTable taps;
 };
+
+// Quantised-row workspace.  MuLUT.InterpTorchBatch re-quantises the whole table on every call
+// (model.py:74-76); K4 does it ONCE per stage and direction into int8 rows, so a vertex row of the
+// x4 tables is one 16-byte load instead of 16 scalar fp32 loads + 16 rint/clamp (ncu: the fp32
+// version was L1-bound at 92 %, 31 sectors per request).
+__host__ __device__ constexpr int q_pitch(int up) { return up == 1 ? 1 : up == 2 ? 4 : up == 3 ? 12 : 16; }
+static size_t align16(size_t b) { return (b + 15) / 16 * 16; }
+static size_t stage_ws_mode_bytes(int n_rows, int up) { return align16((size_t)n_rows * q_pitch(up)) + align16((size_t)n_rows * 2); }
+
+template <int UP>
+__global__ void __launch_bounds__(256)
+quantize_rows_kernel(const float *__restrict__ w, int n_rows, int8_t *__restrict__ q, uint16_t *__restrict__ flag)
+{
+    constexpr int UP2 = UP * UP, RB = q_pitch(UP);
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
+        uint32_t f = 0;
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            int8_t v = 0;
+            if (j < UP2) {
+                const float x = __ldg(w + (size_t)r * UP2 + j);
+                v = (int8_t)(int)quant(x);
+                f |= (quant_pass(x) ? 1u : 0u) << j;
+            }
+            q[(size_t)r * RB + j] = v;
+        }
+        flag[r] = (uint16_t)f;
+    }
+}
+
+template <int UP>
+__device__ __forceinline__ void load_qrow(const int8_t *__restrict__ q, int row, int (&v)[UP * UP])
+{
+    if constexpr (UP == 1) {
+        v[0] = __ldg(q + row);
+    } else if constexpr (UP == 2) {
+        const int w = __ldg(reinterpret_cast<const int *>(q) + row);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (int)(int8_t)(w >> (8 * j));
+    } else if constexpr (UP == 3) {
+        const int *p = reinterpret_cast<const int *>(q + (size_t)row * 12);
+        const int w[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+#pragma unroll
+        for (int j = 0; j < 9; ++j) v[j] = (int)(int8_t)(w[j >> 2] >> (8 * (j & 3)));
+    } else {
+        const int4 w4 = __ldg(reinterpret_cast<const int4 *>(q) + row);
+        const int w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (int)(int8_t)(w[j >> 2] >> (8 * (j & 3)));
+    }
+}
 
 // simplex of four tap VALUES (model.py:122-160 without the pad/rotate bookkeeping)
 __device__ __forceinline__ void simplex_from_taps(const float (&t)[4], int interval, int n_rows, Simplex &s)
@@ -335,7 +388,7 @@ stage_fwd_kernel(const __grid_constant__ StageF32Args a, float *__restrict__ out
 #pragma unroll
         for (int j = 0; j < UP2; ++j) pred[j] = 0.f;
         for (int m = 0; m < a.n_modes; ++m) {
-            const float *__restrict__ W = a.weight[m];
+            const int8_t *__restrict__ Q = a.wq[m];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 float t[4];
@@ -347,20 +400,24 @@ stage_fwd_kernel(const __grid_constant__ StageF32Args a, float *__restrict__ out
                 }
                 Simplex s;
                 simplex_from_taps(t, a.interval, a.n_rows, s);
-                float o[UP2];
+                // weights and quantised LUT values are small integers: the sum is exact in int32
+                // (and equal to the reference's fp32 sum, |o| <= q * 127)
+                int o[UP2];
 #pragma unroll
-                for (int j = 0; j < UP2; ++j) o[j] = 0.f;
+                for (int j = 0; j < UP2; ++j) o[j] = 0;
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
-                    const float *__restrict__ row = W + (size_t)s.v[k] * UP2;
+                    int qv[UP2];
+                    load_qrow<UP>(Q, s.v[k], qv);
+                    const int wk = (int)s.w[k];
 #pragma unroll
-                    for (int j = 0; j < UP2; ++j) o[j] = __fadd_rn(o[j], __fmul_rn(s.w[k], quant(__ldg(row + j))));
+                    for (int j = 0; j < UP2; ++j) o[j] += wk * qv[j];
                 }
                 // pred += rot_back(o / q); pred = round(pred)   (model.py:306-308, half-to-even)
 #pragma unroll
                 for (int j = 0; j < UP2; ++j) {
                     const int p = subpixel_perm<UP>(r, j);
-                    pred[p] = rintf(__fadd_rn(pred[p], __fmul_rn(o[j], inv_q)));
+                    pred[p] = rintf(__fadd_rn(pred[p], __fmul_rn((float)o[j], inv_q)));
                 }
             }
         }
@@ -409,7 +466,8 @@ stage_bwd_kernel(const __grid_constant__ StageF32Args a, const float *__restrict
                 g[u * UP + v] = mask[o_idx] ? __fdiv_rn(__ldg(gout + o_idx), a.avg) * inv_q : 0.f;
             }
         for (int m = 0; m < a.n_modes; ++m) {
-            const float *__restrict__ W = a.weight[m];
+            const int8_t *__restrict__ Q = a.wq[m];
+            const uint16_t *__restrict__ FL = a.wflag[m];
             float *__restrict__ GW = a.gweight[m];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -430,14 +488,13 @@ stage_bwd_kernel(const __grid_constant__ StageF32Args a, const float *__restrict
                 float dot_prev = 0.f;
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
-                    const float *__restrict__ row = W + (size_t)s.v[k] * UP2;
-                    float wraw[UP2];
-#pragma unroll
-                    for (int j = 0; j < UP2; ++j) wraw[j] = __ldg(row + j);
+                    int qv[UP2];
+                    load_qrow<UP>(Q, s.v[k], qv);
                     float dot = 0.f;
 #pragma unroll
-                    for (int j = 0; j < UP2; ++j) dot += gr[j] * quant(wraw[j]);
+                    for (int j = 0; j < UP2; ++j) dot += gr[j] * (float)qv[j];
                     if (GW) {
+                        const uint32_t fl = __ldg(FL + s.v[k]);
                         float *__restrict__ gw = GW + (size_t)s.v[k] * UP2;
                         if constexpr (UP2 % 4 == 0) {
 #pragma unroll
@@ -445,13 +502,13 @@ stage_bwd_kernel(const __grid_constant__ StageF32Args a, const float *__restrict
                                 float c[4];
 #pragma unroll
                                 for (int e = 0; e < 4; ++e)
-                                    c[e] = quant_pass(wraw[j + e]) ? 127.f * (s.w[k] * gr[j + e]) : 0.f;
+                                    c[e] = ((fl >> (j + e)) & 1u) ? 127.f * (s.w[k] * gr[j + e]) : 0.f;
                                 red_add_v4(gw + j, c[0], c[1], c[2], c[3]);
                             }
                         } else {
 #pragma unroll
                             for (int j = 0; j < UP2; ++j)
-                                if (quant_pass(wraw[j])) atomicAdd(gw + j, 127.f * (s.w[k] * gr[j]));
+                                if ((fl >> j) & 1u) atomicAdd(gw + j, 127.f * (s.w[k] * gr[j]));
                         }
                     }
                     if (gx && k > 0) {
@@ -478,8 +535,11 @@ stage_bwd_kernel(const __grid_constant__ StageF32Args a, const float *__restrict
 }
 
 static int fill_stage_args(StageF32Args &a, const float *const *weights, int n_modes, const char *modes, int n_rows,
-                           int up, int interval, const float *x, int B, int C, int h, int w, float avg, float bias)
+                           int up, int interval, const float *x, int B, int C, int h, int w, float avg, float bias,
+                           void *workspace)
 {
+    if (!workspace) { set_error("stage: null workspace (mulut_stage_workspace_bytes)"); return MULUT_E_BAD_ARG; }
+    if (reinterpret_cast<uintptr_t>(workspace) & 15) { set_error("stage: workspace must be 16-byte aligned"); return MULUT_E_BAD_ARG; }
     if (!weights || !modes || !x || n_modes < 1 || n_modes > MULUT_MAX_MODES || B < 0 || C < 0 || h < 0 || w < 0 ||
         interval < 1 || interval > 7 || !(avg > 0.f)) {
         set_error("stage: bad argument");
@@ -502,6 +562,9 @@ static int fill_stage_args(StageF32Args &a, const float *const *weights, int n_m
     for (int m = 0; m < n_modes; ++m) {
         if (!weights[m]) { set_error("stage: weights[%d] is null", m); return MULUT_E_BAD_ARG; }
         a.weight[m] = weights[m];
+        uint8_t *base = static_cast<uint8_t *>(workspace) + (size_t)m * stage_ws_mode_bytes(n_rows, up);
+        a.wq[m] = reinterpret_cast<const int8_t *>(base);
+        a.wflag[m] = reinterpret_cast<const uint16_t *>(base + align16((size_t)n_rows * q_pitch(up)));
     }
     a.x = x; a.BC = B * C; a.h = h; a.w = w; a.n_modes = n_modes; a.interval = interval; a.n_rows = n_rows;
     a.avg = avg; a.bias = bias;
@@ -607,17 +670,35 @@ extern "C" int mulut_interp_pass_f64(const float *d_weight, int n_rows, const fl
     return MULUT_OK;
 }
 
+extern "C" size_t mulut_stage_workspace_bytes(int n_modes, int n_rows, int up)
+{
+    if (n_modes < 1 || n_rows < 1 || up < 1 || up > 4) return 0;
+    return (size_t)n_modes * stage_ws_mode_bytes(n_rows, up);
+}
+
 extern "C" int mulut_stage_fwd_f32(const float *const *d_weights, int n_modes, const char *modes, int n_rows, int up,
                                    int interval, const float *d_x, int B, int C, int h, int w, float avg, float bias,
-                                   float *d_out, uint8_t *d_mask, void *stream)
+                                   float *d_out, uint8_t *d_mask, void *d_workspace, void *stream)
 {
     StageF32Args a;
-    int rc = fill_stage_args(a, d_weights, n_modes, modes, n_rows, up, interval, d_x, B, C, h, w, avg, bias);
+    int rc = fill_stage_args(a, d_weights, n_modes, modes, n_rows, up, interval, d_x, B, C, h, w, avg, bias, d_workspace);
     if (rc) return rc;
     if (!d_out || !d_mask) { set_error("stage_fwd: null output"); return MULUT_E_BAD_ARG; }
     const size_t total = (size_t)B * C * h * w;
-    if (total == 0) return MULUT_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    for (int m = 0; m < n_modes; ++m) {          // quantise the tables once for this stage (read again by the backward)
+        int8_t *q = const_cast<int8_t *>(a.wq[m]);
+        uint16_t *f = const_cast<uint16_t *>(a.wflag[m]);
+        const unsigned qb = (unsigned)((n_rows + 255) / 256);
+        switch (up) {
+        case 1: quantize_rows_kernel<1><<<qb, 256, 0, st>>>(a.weight[m], n_rows, q, f); break;
+        case 2: quantize_rows_kernel<2><<<qb, 256, 0, st>>>(a.weight[m], n_rows, q, f); break;
+        case 3: quantize_rows_kernel<3><<<qb, 256, 0, st>>>(a.weight[m], n_rows, q, f); break;
+        default: quantize_rows_kernel<4><<<qb, 256, 0, st>>>(a.weight[m], n_rows, q, f); break;
+        }
+    }
+    MULUT_CUDA(cudaGetLastError());
+    if (total == 0) return MULUT_OK;
     switch (up) {
     case 1: stage_fwd_kernel<1><<<grid_for(total), 256, 0, st>>>(a, d_out, d_mask); break;
     case 2: stage_fwd_kernel<2><<<grid_for(total), 256, 0, st>>>(a, d_out, d_mask); break;
@@ -630,11 +711,12 @@ extern "C" int mulut_stage_fwd_f32(const float *const *d_weights, int n_modes, c
 
 extern "C" int mulut_stage_bwd_f32(const float *const *d_weights, int n_modes, const char *modes, int n_rows, int up,
                                    int interval, const float *d_x, int B, int C, int h, int w, float avg, float bias,
-                                   const float *d_grad_out, const uint8_t *d_mask, float *const *d_grad_weights,
-                                   float *d_grad_x, void *stream)
+                                   const float *d_grad_out, const uint8_t *d_mask, const void *d_workspace,
+                                   float *const *d_grad_weights, float *d_grad_x, void *stream)
 {
     StageF32Args a;
-    int rc = fill_stage_args(a, d_weights, n_modes, modes, n_rows, up, interval, d_x, B, C, h, w, avg, bias);
+    int rc = fill_stage_args(a, d_weights, n_modes, modes, n_rows, up, interval, d_x, B, C, h, w, avg, bias,
+                             const_cast<void *>(d_workspace));
     if (rc) return rc;
     if (!d_grad_out || !d_mask) { set_error("stage_bwd: null grad_out / mask"); return MULUT_E_BAD_ARG; }
     bool any = d_grad_x != nullptr;

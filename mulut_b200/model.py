@@ -73,19 +73,22 @@ class _StageFunction(torch.autograd.Function):
         B, C, h, wd = xs.shape
         out = torch.empty((B, C, h * upscale, wd * upscale), dtype=torch.float32, device=xs.device)
         mask = torch.empty(out.shape, dtype=torch.uint8, device=xs.device)
+        # quantised int8 rows + clamp flags of this stage's tables: written by the forward, re-read by the backward
+        qws = torch.empty(_lib.lib().mulut_stage_workspace_bytes(len(ws), ws[0].shape[0], upscale), dtype=torch.uint8,
+                          device=xs.device)
         ptrs = (ctypes.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
         stream = ctypes.c_void_p(torch.cuda.current_stream(xs.device).cuda_stream)
         with torch.cuda.device(xs.device):
             _lib.check(_lib.lib().mulut_stage_fwd_f32(ptrs, len(ws), modes.encode(), ws[0].shape[0], upscale, interval,
                                                       xs.data_ptr(), B, C, h, wd, float(avg), float(bias),
-                                                      out.data_ptr(), mask.data_ptr(), stream))
-        ctx.save_for_backward(xs, mask, *ws)
+                                                      out.data_ptr(), mask.data_ptr(), qws.data_ptr(), stream))
+        ctx.save_for_backward(xs, mask, qws, *ws)
         ctx.cfg = (upscale, modes, float(avg), float(bias), interval)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        xs, mask, *ws = ctx.saved_tensors
+        xs, mask, qws, *ws = ctx.saved_tensors
         upscale, modes, avg, bias, interval = ctx.cfg
         B, C, h, wd = xs.shape
         g = grad_out.contiguous().float()
@@ -97,7 +100,7 @@ class _StageFunction(torch.autograd.Function):
         with torch.cuda.device(xs.device):
             _lib.check(_lib.lib().mulut_stage_bwd_f32(ptrs, len(ws), modes.encode(), ws[0].shape[0], upscale, interval,
                                                       xs.data_ptr(), B, C, h, wd, avg, bias, g.data_ptr(),
-                                                      mask.data_ptr(), gptrs,
+                                                      mask.data_ptr(), qws.data_ptr(), gptrs,
                                                       gx.data_ptr() if gx is not None else None, stream))
         return (gx, None, None, None, None, None) + tuple(gws)
 

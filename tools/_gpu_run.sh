@@ -1,6 +1,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_finetune.py -x -q -m gpu > gpurun_out/pytest_ft.log 2>&1; echo "pytest rc=$?"
-tail -15 gpurun_out/pytest_ft.log
+tail -5 gpurun_out/pytest_ft.log
 timeout 300 python tools/finetune_bench.py --steps 10 > gpurun_out/finetune_fused.json 2>gpurun_out/ft.err; tail -2 gpurun_out/ft.err; cat gpurun_out/finetune_fused.json
-timeout 300 python tools/finetune_bench.py --steps 10 --loop > gpurun_out/finetune_loop.json 2>gpurun_out/ft.err; tail -2 gpurun_out/ft.err; cat gpurun_out/finetune_loop.json
