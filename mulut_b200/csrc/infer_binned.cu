@@ -202,33 +202,43 @@ bin_collect_kernel(const uint8_t *__restrict__ img, size_t total, BinCtl *__rest
     const size_t n16 = total / 16;
     const uint4 *__restrict__ v = reinterpret_cast<const uint4 *>(img);
     const int lane = threadIdx.x & 31;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n16; i0 += stride) {
-        const size_t i = i0 + lane;
-        uint32_t hits = 0;
-        if (i < n16) {
-            const uint4 q = __ldg(v + i);
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    constexpr int U = 4;                                     // independent 16-byte loads in flight per thread
+    const size_t stride = (size_t)gridDim.x * blockDim.x * U;
+    for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * U; i0 < n16; i0 += stride) {
+        uint4 q[U];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) hits |= ((mask >> ((w[k] >> (8 * e + 5)) & 7u)) & 1u) << (4 * k + e);
+        for (int u = 0; u < U; ++u) {
+            const size_t i = i0 + u * 32 + lane;
+            q[u] = i < n16 ? __ldg(v + i) : make_uint4(0, 0, 0, 0);
         }
-        const uint32_t cnt = __popc(hits);
-        uint32_t incl = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        uint32_t base = 0;
-        if (lane == 31 && incl) base = atomicAdd(&ctl->list_count, incl);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        uint32_t pos = base + incl - cnt;
-        while (hits) {
-            const int e = __ffs(hits) - 1;
-            hits &= hits - 1;
-            list[pos++] = (uint32_t)(i * 16 + e);
+        for (int u = 0; u < U; ++u) {
+            const size_t i = i0 + u * 32 + lane;
+            uint32_t hits = 0;
+            if (i < n16) {
+                const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) hits |= ((mask >> ((w[k] >> (8 * e + 5)) & 7u)) & 1u) << (4 * k + e);
+            }
+            if (!__any_sync(0xffffffffu, hits != 0)) continue;
+            const uint32_t cnt = __popc(hits);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            uint32_t base = 0;
+            if (lane == 31) base = atomicAdd(&ctl->list_count, incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint32_t pos = base + incl - cnt;
+            while (hits) {
+                const int e = __ffs(hits) - 1;
+                hits &= hits - 1;
+                list[pos++] = (uint32_t)(i * 16 + e);
+            }
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
