@@ -169,6 +169,16 @@ int mulut_stage_bwd_f32(const float *const *d_weights, int n_modes, const char *
                         const void *d_workspace, float *const *d_grad_weights, float *d_grad_x,
                         void *stream);
 
+/*
+ * On-device report metrics of eltr._worker, sr/4_test_lut.py:309-314: PSNR and SSIM on the BT.601
+ * luma of two RGB uint8 frames, definitions of common/utils.py:42-101 (_rgb2ycbcr, PSNR with
+ * shave_border, cal_ssim: 11x11 Gaussian window sigma 1.5, 'valid', float64).
+ *   d_gt, d_img  uint8 (H, W, 3) device frames;  d_work  32 bytes of device scratch
+ *   out2         HOST: {PSNR in dB, mean SSIM}.  Synchronous on `stream`.
+ */
+int mulut_eval_psnr_ssim_y_u8(const uint8_t *d_gt, const uint8_t *d_img, int H, int W, int shave_border,
+                              void *d_work, double *out2, void *stream);
+
 /* Pinned host memory for the *_host entry points. */
 void *mulut_host_alloc(size_t bytes);
 int mulut_host_free(void *p);

@@ -248,8 +248,12 @@ class eltr:
         self.engine = LutEngine(lutDict, opt.stages, opt.modes, opt.scale, opt.interval, device=device)
 
     def run(self, num_worker=None):
-        from .metrics import PSNR, cal_ssim, modcrop, rgb2ycbcr
+        """PSNR / SSIM are computed on the GPU (mulut_eval_psnr_ssim_y_u8) from the device-resident
+        SR frame and the uploaded HR frame; the SR frame comes back once, for the PNG."""
+        import torch
+        from .metrics import modcrop, psnr_ssim_device
         from PIL import Image
+        dev = torch.device("cuda", self.engine.device)
         res = []
         for name in self.files:
             lr = np.array(Image.open(os.path.join(self.opt.testDir, self.dataset,
@@ -260,11 +264,11 @@ class eltr:
                          self.opt.scale)
             if gt.ndim == 2:
                 gt = np.stack([gt] * 3, axis=2)
-            out = self.engine(np.ascontiguousarray(lr[:, :, :3]))
-            Image.fromarray(out).save(os.path.join(
+            d_out = self.engine(torch.from_numpy(np.ascontiguousarray(lr[:, :, :3])).to(dev))
+            d_gt = torch.from_numpy(np.ascontiguousarray(gt[:, :, :3])).to(dev)
+            res.append(list(psnr_ssim_device(d_gt, d_out, self.opt.scale)))
+            Image.fromarray(d_out.cpu().numpy()).save(os.path.join(
                 self.result_path, "{}_{}_{}bit.png".format(name[:-4], self.opt.lutName, 8 - self.opt.interval)))
-            y_gt, y_out = rgb2ycbcr(gt)[:, :, 0], rgb2ycbcr(out)[:, :, 0]
-            res.append([PSNR(y_gt, y_out, self.opt.scale), cal_ssim(y_gt, y_out)])
         res = np.asarray(res)
         print("Dataset {} | AVG LUT PSNR: {:.2f} SSIM: {:.4f}".format(self.dataset, res[:, 0].mean(), res[:, 1].mean()))
         return res

@@ -46,3 +46,23 @@ def cal_ssim(img1, img2) -> float:
     s1, s2, s12 = conv(a * a) - mu1 * mu1, conv(b * b) - mu2 * mu2, conv(a * b) - mu1 * mu2
     m = ((2 * mu1 * mu2 + c1) * (2 * s12 + c2)) / ((mu1 * mu1 + mu2 * mu2 + c1) * (s1 + s2 + c2))
     return float(m.mean())
+
+
+def psnr_ssim_device(gt, img, shave_border: int = 4):
+    """(PSNR, SSIM) on the BT.601 luma of two RGB uint8 CUDA tensors (H,W,3), computed on the GPU
+    (mulut_eval_psnr_ssim_y_u8): the same definitions as PSNR(rgb2ycbcr(.)[..., 0]) and cal_ssim above."""
+    import ctypes
+    import torch
+    from . import _lib
+    if not (isinstance(gt, torch.Tensor) and isinstance(img, torch.Tensor) and gt.is_cuda and img.is_cuda):
+        raise TypeError("psnr_ssim_device expects CUDA uint8 tensors (no CPU fallback; use PSNR / cal_ssim on the host)")
+    if gt.dtype != torch.uint8 or img.dtype != torch.uint8 or gt.shape != img.shape or gt.dim() != 3 or gt.shape[2] != 3:
+        raise ValueError("expected two uint8 (H,W,3) tensors of the same shape")
+    g, s = gt.contiguous(), img.contiguous()
+    work = torch.empty(32, dtype=torch.uint8, device=g.device)
+    out = (ctypes.c_double * 2)()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.lib().mulut_eval_psnr_ssim_y_u8(g.data_ptr(), s.data_ptr(), g.shape[0], g.shape[1],
+                                                        int(shave_border), work.data_ptr(), out, stream))
+    return float(out[0]), float(out[1])
