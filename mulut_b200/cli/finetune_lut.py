@@ -41,9 +41,77 @@ def synthetic_batch(batch: int, crop: int, scale: int, seed: int, device):
     return im.to(device), lb.to(device)
 
 
+class GraphedStep:
+    """One training step of 3_finetune_lut.py:129-136 (zero_grad -> forward -> MSE -> backward ->
+    LUT-gradient all-reduce -> Adam) captured ONCE in a CUDA graph and replayed: the step is ~10
+    kernels of 0.2-1 ms, so the ~60 launches and the autograd bookkeeping of an eager step cost as
+    much host time as the GPU needs.  The learning rate lives in a device tensor (Adam capturable),
+    the batch in static buffers; the warm-up iterations CUDA graphs need are rolled back."""
+
+    def __init__(self, model_G, im_shape, lb_shape, lr0, weight_decay=0.0):
+        import copy
+        device = next(model_G.parameters()).device
+        self.model = model_G
+        self.params = [p for p in model_G.parameters() if p.requires_grad]
+        self.bucket = mdist.FlatGradBucket(self.params)
+        self.lr = torch.tensor(float(lr0), device=device)
+        self.opt = torch.optim.Adam(self.params, lr=self.lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=weight_decay,
+                                    capturable=True)
+        self.im = torch.zeros(im_shape, device=device)
+        self.lb = torch.zeros(lb_shape, device=device)
+        saved = [p.detach().clone() for p in self.params]
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._body()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        with torch.no_grad():                    # roll the warm-up back: parameters and Adam state
+            for p, q in zip(self.params, saved):
+                p.copy_(q)
+            for st in self.opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+
+    def _body(self):
+        self.bucket.zero_()
+        loss = F.mse_loss(self.model(self.im), self.lb)
+        loss.backward()
+        self.bucket.all_reduce_mean()
+        self.opt.step()
+        return loss.detach()
+
+    def __call__(self, im, lb, lr: float):
+        self.im.copy_(im)
+        self.lb.copy_(lb)
+        self.lr.fill_(float(lr))
+        self.graph.replay()
+        return self.loss.clone()                  # device scalar (the graph's output buffer is reused); .item() synchronises
+
+
 def finetune_steps(model_G: MuLUT, steps: int, batch: int, crop: int, seed: int, lr0: float, lr1: float,
-                   total_iter: int, weight_decay: float = 0.0, batches=None):
-    """The training loop body of 3_finetune_lut.py:118-136 on this rank's share."""
+                   total_iter: int, weight_decay: float = 0.0, batches=None, graph: bool = False):
+    """The training loop body of 3_finetune_lut.py:118-136 on this rank's share.
+    graph=True replays the step as one CUDA graph (same arithmetic; needs a fixed batch shape)."""
+    if graph:
+        rank, world, _ = mdist.env_rank_world()
+        device = next(model_G.parameters()).device
+        r = model_G.upscale
+        C = 1 if batches is None else batches[0][0].shape[1]
+        b0 = batch if batches is None else batches[0][0].shape[0]
+        model_G.train()
+        gs = GraphedStep(model_G, (b0, C, crop, crop), (b0, C, crop * r, crop * r), lr0, weight_decay)
+        lam = lr_lambda(total_iter, lr0, lr1)
+        losses = []
+        for i in range(steps):
+            im, lb = batches[i] if batches is not None else synthetic_batch(batch, crop, r, seed + i * world + rank, device)
+            losses.append(gs(im, lb, lr0 * lam(i)))     # LambdaLR: lr of step i is lr0 * lambda(i)
+        return [float(l) for l in torch.stack(losses).cpu()] if losses else []
     rank, world, _ = mdist.env_rank_world()
     device = next(model_G.parameters()).device
     params = [p for p in model_G.parameters() if p.requires_grad]
@@ -82,7 +150,7 @@ def main(argv=None):
     per_rank = max(1, opt.batchSize // world)
     st = time.time()
     losses = finetune_steps(model_G, opt.totalIter, per_rank, opt.cropSize, 0, opt.lr0, opt.lr1, opt.totalIter,
-                            opt.weightDecay)
+                            opt.weightDecay, graph=not getattr(opt, "eager", False))
     if rank == 0:
         print("{} | Iter:{:6d}, loss:{:.3e}, rT:{:.4f}".format(opt.expDir, opt.totalIter, np.mean(losses[-100:]),
                                                           (time.time() - st) / max(1, opt.totalIter)))

@@ -8,6 +8,8 @@
 //
 // The reference enumerates 24 strict-inequality cases; that is a descending
 // sort of the four fractions with ties broken "higher tap index first".
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mulut {
@@ -271,6 +273,8 @@ struct StageF32Args {
     const float *x;                          // (BC, h, w), integer-valued 0..255
     int BC, h, w, n_modes, interval, n_rows;
     float avg, bias;
+    int aggregate;                           // backward: 0 direct reds, 1 warp-aggregated, 2 decide from `stats`
+    uint32_t *stats;                         // workspace tail: {lanes sharing their first LUT row with another lane, lanes}
     const float *weight[MULUT_MAX_MODES];    // raw parameters (n_rows, up^2)
     const int8_t *wq[MULUT_MAX_MODES];       // quantised once per call: clamp(rint(w*127), +-127), rows of q_pitch(up) bytes
     const uint16_t *wflag[MULUT_MAX_MODES];  // bit j: the clamp passes the gradient of column j (|rint(w*127)| <= 127)
@@ -285,12 +289,15 @@ struct StageF32Args {
 __host__ __device__ constexpr int q_pitch(int up) { return up == 1 ? 1 : up == 2 ? 4 : up == 3 ? 12 : 16; }
 static size_t align16(size_t b) { return (b + 15) / 16 * 16; }
 static size_t stage_ws_mode_bytes(int n_rows, int up) { return align16((size_t)n_rows * q_pitch(up)) + align16((size_t)n_rows * 2); }
+constexpr size_t STAGE_WS_TAIL = 16;       // row-sharing statistics of the forward pass (see StageF32Args::stats)
 
 template <int UP>
 __global__ void __launch_bounds__(256)
-quantize_rows_kernel(const float *__restrict__ w, int n_rows, int8_t *__restrict__ q, uint16_t *__restrict__ flag)
+quantize_rows_kernel(const float *__restrict__ w, int n_rows, int8_t *__restrict__ q, uint16_t *__restrict__ flag,
+                     uint32_t *__restrict__ stats_to_clear)
 {
     constexpr int UP2 = UP * UP, RB = q_pitch(UP);
+    if (stats_to_clear && blockIdx.x == 0 && threadIdx.x < 4) stats_to_clear[threadIdx.x] = 0u;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
         uint32_t f = 0;
 #pragma unroll
@@ -400,6 +407,17 @@ stage_fwd_kernel(const __grid_constant__ StageF32Args a, float *__restrict__ out
                 }
                 Simplex s;
                 simplex_from_taps(t, a.interval, a.n_rows, s);
+                if (m == 0 && r == 0) {
+                    // how many lanes share their first LUT row with another lane of the warp: the backward
+                    // uses it to choose between direct and warp-aggregated gradient scatter
+                    const unsigned am = __activemask();
+                    const unsigned peers = __match_any_sync(am, s.v[0]);
+                    const unsigned shared_rows = __ballot_sync(am, (peers & (peers - 1u)) != 0u);
+                    if ((threadIdx.x & 31) == (unsigned)(__ffs(am) - 1)) {
+                        atomicAdd(a.stats, (uint32_t)__popc(shared_rows));
+                        atomicAdd(a.stats + 1, (uint32_t)__popc(am));
+                    }
+                }
                 // weights and quantised LUT values are small integers: the sum is exact in int32
                 // (and equal to the reference's fp32 sum, |o| <= q * 127)
                 int o[UP2];
@@ -434,16 +452,46 @@ stage_fwd_kernel(const __grid_constant__ StageF32Args a, float *__restrict__ out
     }
 }
 
+// Warp-aggregated scatter: lanes of a warp that update the SAME LUT row (natural patches sit on
+// the LUT diagonal: neighbouring pixels share cell and fraction order) merge their contributions
+// through shuffles - a tree over the peers found by match.any - and only the first peer issues the
+// red.  When every lane has a row of its own (uniform random patches) the cost is one match + one vote.
+// Returns true on the lane that must issue the update; c[] then holds the group's sum.
+template <int N>
+__device__ __noinline__ bool warp_merge_tree(unsigned active, unsigned peers, float *c)
+{
+    const int lane = threadIdx.x & 31;
+    const int rel = __popc(peers & ((1u << lane) - 1u));        // my rank among the peers
+    const int size = __popc(peers);
+    for (int s = 1; s < 32; s <<= 1) {
+        if (!__any_sync(active, size > s)) break;
+        const unsigned src = __fns(peers, 0, rel + s + 1);       // lane of the peer ranked rel + s (or ~0u)
+        const bool take = ((rel & (2 * s - 1)) == 0) && (src != 0xffffffffu);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const float v = __shfl_sync(active, c[j], take ? (int)src : lane);
+            if (take) c[j] += v;
+        }
+    }
+    return rel == 0;
+}
+
+template <int N>
+__device__ __forceinline__ bool warp_merge_rows(unsigned active, int row, float (&c)[N])
+{
+    const unsigned peers = __match_any_sync(active, row);
+    if (!__any_sync(active, (peers & (peers - 1u)) != 0u)) return true;     // every lane alone: nothing to merge
+    return warp_merge_tree<N>(active, peers, c);                            // out of line: keeps the unrolled passes small
+}
+
 constexpr int K4_T = 16;                 // backward tile: 16 x 16 input pixels per CTA
 constexpr int K4_P = K4_T + 4;           // + 2-pixel halo on every side
 
-template <int UP>
-__global__ void __launch_bounds__(K4_T * K4_T)
-stage_bwd_kernel(const __grid_constant__ StageF32Args a, const float *__restrict__ gout,
-                 const uint8_t *__restrict__ mask, float *__restrict__ gx)
+template <int UP, bool AGG>
+__device__ __forceinline__ void stage_bwd_body(const StageF32Args &a, const float *__restrict__ gout,
+                                               const uint8_t *__restrict__ mask, float *__restrict__ gx, float *s_gx)
 {
     constexpr int UP2 = UP * UP;
-    __shared__ float s_gx[K4_P * K4_P];
     const int tiles_x = (a.w + K4_T - 1) / K4_T, tiles_y = (a.h + K4_T - 1) / K4_T;
     const int tx = blockIdx.x % tiles_x;
     const int ty = (blockIdx.x / tiles_x) % tiles_y;
@@ -454,6 +502,7 @@ stage_bwd_kernel(const __grid_constant__ StageF32Args a, const float *__restrict
     for (int i = threadIdx.x; i < K4_P * K4_P; i += blockDim.x) s_gx[i] = 0.f;
     __syncthreads();
 
+    const unsigned active = __ballot_sync(0xffffffffu, x < a.w && y < a.h);   // lanes that own a pixel
     if (x < a.w && y < a.h) {
         const float *__restrict__ plane = a.x + bc * (size_t)a.h * a.w;
         // g = dL/d(o)  = G * mask / avg / q   (o enters pred as o/q; the rounds are identity)
@@ -496,19 +545,19 @@ stage_bwd_kernel(const __grid_constant__ StageF32Args a, const float *__restrict
                     if (GW) {
                         const uint32_t fl = __ldg(FL + s.v[k]);
                         float *__restrict__ gw = GW + (size_t)s.v[k] * UP2;
-                        if constexpr (UP2 % 4 == 0) {
+                        // d/dweight = 127 * [clamp passes] * (w_k / q) * g   (straight-through quantiser)
+                        float c[UP2];
 #pragma unroll
-                            for (int j = 0; j < UP2; j += 4) {
-                                float c[4];
+                        for (int j = 0; j < UP2; ++j) c[j] = ((fl >> j) & 1u) ? 127.f * (s.w[k] * gr[j]) : 0.f;
+                        if (!AGG || warp_merge_rows<UP2>(active, s.v[k], c)) {
+                            if constexpr (UP2 % 4 == 0) {
 #pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    c[e] = ((fl >> (j + e)) & 1u) ? 127.f * (s.w[k] * gr[j + e]) : 0.f;
-                                red_add_v4(gw + j, c[0], c[1], c[2], c[3]);
+                                for (int j = 0; j < UP2; j += 4) red_add_v4(gw + j, c[j], c[j + 1], c[j + 2], c[j + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < UP2; ++j)
+                                    if (c[j] != 0.f) atomicAdd(gw + j, c[j]);
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < UP2; ++j)
-                                if ((fl >> j) & 1u) atomicAdd(gw + j, 127.f * (s.w[k] * gr[j]));
                         }
                     }
                     if (gx && k > 0) {
@@ -532,6 +581,18 @@ stage_bwd_kernel(const __grid_constant__ StageF32Args a, const float *__restrict
             if (v != 0.f && yy >= 0 && yy < a.h && xx >= 0 && xx < a.w) atomicAdd(gplane + (size_t)yy * a.w + xx, v);
         }
     }
+}
+
+template <int UP>
+__global__ void __launch_bounds__(K4_T * K4_T)
+stage_bwd_kernel(const __grid_constant__ StageF32Args a, const float *__restrict__ gout,
+                 const uint8_t *__restrict__ mask, float *__restrict__ gx)
+{
+    __shared__ float s_gx[K4_P * K4_P];
+    // aggregate when more than a quarter of the forward's lanes shared a LUT row with a neighbour
+    const bool agg = a.aggregate == 2 ? (4ull * a.stats[0] > (unsigned long long)a.stats[1]) : a.aggregate != 0;
+    if (agg) stage_bwd_body<UP, true>(a, gout, mask, gx, s_gx);
+    else stage_bwd_body<UP, false>(a, gout, mask, gx, s_gx);
 }
 
 static int fill_stage_args(StageF32Args &a, const float *const *weights, int n_modes, const char *modes, int n_rows,
@@ -566,6 +627,7 @@ static int fill_stage_args(StageF32Args &a, const float *const *weights, int n_m
         a.wq[m] = reinterpret_cast<const int8_t *>(base);
         a.wflag[m] = reinterpret_cast<const uint16_t *>(base + align16((size_t)n_rows * q_pitch(up)));
     }
+    a.stats = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(workspace) + (size_t)n_modes * stage_ws_mode_bytes(n_rows, up));
     a.x = x; a.BC = B * C; a.h = h; a.w = w; a.n_modes = n_modes; a.interval = interval; a.n_rows = n_rows;
     a.avg = avg; a.bias = bias;
     return MULUT_OK;
@@ -673,7 +735,7 @@ extern "C" int mulut_interp_pass_f64(const float *d_weight, int n_rows, const fl
 extern "C" size_t mulut_stage_workspace_bytes(int n_modes, int n_rows, int up)
 {
     if (n_modes < 1 || n_rows < 1 || up < 1 || up > 4) return 0;
-    return (size_t)n_modes * stage_ws_mode_bytes(n_rows, up);
+    return (size_t)n_modes * stage_ws_mode_bytes(n_rows, up) + STAGE_WS_TAIL;
 }
 
 extern "C" int mulut_stage_fwd_f32(const float *const *d_weights, int n_modes, const char *modes, int n_rows, int up,
@@ -691,10 +753,10 @@ extern "C" int mulut_stage_fwd_f32(const float *const *d_weights, int n_modes, c
         uint16_t *f = const_cast<uint16_t *>(a.wflag[m]);
         const unsigned qb = (unsigned)((n_rows + 255) / 256);
         switch (up) {
-        case 1: quantize_rows_kernel<1><<<qb, 256, 0, st>>>(a.weight[m], n_rows, q, f); break;
-        case 2: quantize_rows_kernel<2><<<qb, 256, 0, st>>>(a.weight[m], n_rows, q, f); break;
-        case 3: quantize_rows_kernel<3><<<qb, 256, 0, st>>>(a.weight[m], n_rows, q, f); break;
-        default: quantize_rows_kernel<4><<<qb, 256, 0, st>>>(a.weight[m], n_rows, q, f); break;
+        case 1: quantize_rows_kernel<1><<<qb, 256, 0, st>>>(a.weight[m], n_rows, q, f, m == 0 ? a.stats : nullptr); break;
+        case 2: quantize_rows_kernel<2><<<qb, 256, 0, st>>>(a.weight[m], n_rows, q, f, m == 0 ? a.stats : nullptr); break;
+        case 3: quantize_rows_kernel<3><<<qb, 256, 0, st>>>(a.weight[m], n_rows, q, f, m == 0 ? a.stats : nullptr); break;
+        default: quantize_rows_kernel<4><<<qb, 256, 0, st>>>(a.weight[m], n_rows, q, f, m == 0 ? a.stats : nullptr); break;
         }
     }
     MULUT_CUDA(cudaGetLastError());
@@ -720,6 +782,7 @@ extern "C" int mulut_stage_bwd_f32(const float *const *d_weights, int n_modes, c
     if (rc) return rc;
     if (!d_grad_out || !d_mask) { set_error("stage_bwd: null grad_out / mask"); return MULUT_E_BAD_ARG; }
     bool any = d_grad_x != nullptr;
+    { const char *e = getenv("MULUT_K4_AGGREGATE"); a.aggregate = e ? atoi(e) : 2; }   // 0 / 1 force, default: decide from the forward's statistic
     for (int m = 0; m < n_modes; ++m) {
         a.gweight[m] = d_grad_weights ? d_grad_weights[m] : nullptr;
         any |= a.gweight[m] != nullptr;

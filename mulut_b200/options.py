@@ -92,6 +92,8 @@ class TrainOptions:
         p.add_argument("--workerNum", "-n", type=int, default=8)
         p.add_argument("--synthetic", action="store_true", default=False,
                        help="train on seeded synthetic patches (no dataset on disk)")
+        p.add_argument("--eager", action="store_true", default=False,
+                       help="launch every kernel of a step from Python instead of replaying one CUDA graph")
         return p
 
     def parse(self, argv=None):

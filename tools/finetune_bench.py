@@ -34,9 +34,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=256, help="GLOBAL batch (split across ranks)")
     ap.add_argument("--crop", type=int, default=48)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--aten", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="eager launches with per-phase CUDA events instead of the CUDA-graph step")
+    ap.add_argument("--smooth", action="store_true", help="low-frequency patches (neighbouring pixels share LUT rows, like natural images) instead of uniform noise")
     ap.add_argument("--loop", action="store_true", help="reference-style loop of 24 InterpTorchBatch calls (K2/K3) instead of the fused stages (K4)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -57,6 +59,11 @@ def main():
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lr_lambda(200000, 1e-3, 1e-4))
     per_rank = args.batch // world
     im, lb = synthetic_batch(per_rank, args.crop, 4, 1000 + rank, dev)
+    if args.smooth:
+        g = torch.Generator(device="cpu").manual_seed(7 + rank)
+        coarse = torch.randint(0, 256, (per_rank, 1, args.crop // 8 + 2, args.crop // 8 + 2), generator=g).float()
+        im = torch.round(F.interpolate(coarse, scale_factor=8, mode="bilinear", align_corners=False)[..., :args.crop, :args.crop]
+                         .clamp(0, 255)).div(255.0).to(dev).contiguous()
 
     def step(timers=None):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
@@ -78,23 +85,42 @@ def main():
                 timers[k] += ev[i].elapsed_time(ev[i + 1])
         return loss
 
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     timers = {"fwd": 0.0, "bwd": 0.0, "allreduce": 0.0, "adam": 0.0}
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        loss = step(timers)
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / args.steps
+    if args.eager:
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            loss = step(timers)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+    else:
+        # the product path: the whole step replayed as one CUDA graph, timed on the device
+        from mulut_b200.cli.finetune_lut import GraphedStep
+        gs = GraphedStep(net, tuple(im.shape), tuple(lb.shape), 1e-3)
+        for _ in range(args.warmup):
+            gs(im, lb, 1e-3)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss = gs(im, lb, 1e-3)
+        e1.record()
+        torch.cuda.synchronize()
+        dt = e0.elapsed_time(e1) * 1e-3 / args.steps
     t = torch.tensor([dt], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    res = {"workload": "cfg4 finetune step, global batch {} of {}x{} patches, x4 sdy 2-stage".format(args.batch, args.crop, args.crop),
+    res = {"workload": "cfg4 finetune step, global batch {} of {}x{} patches ({}), x4 sdy 2-stage".format(
+        args.batch, args.crop, args.crop, "smooth" if args.smooth else "uniform noise"),
            "n_gpus": world, "ms_per_step": float(t.item()) * 1e3, "patches_per_s": args.batch / float(t.item()),
-           "breakdown_ms": {k: v / args.steps for k, v in timers.items()}, "loss": float(loss.item()),
+           "mode": "eager" if args.eager else "cuda graph",
+           "breakdown_ms": {k: v / args.steps for k, v in timers.items()} if args.eager else None, "loss": float(loss.item()),
            "allreduce_bytes": bucket.flat.numel() * 4}
 
     if args.aten and rank == 0:
