@@ -75,8 +75,28 @@ def make_luts(seed=1):
     return luts
 
 
+DATA = "uniform"
+
+
 def make_frames(n, seed):
-    return np.random.default_rng(seed).integers(0, 256, (n, H, W, C), dtype=np.uint8)
+    """uniform: i.i.d. uint8 (worst case: every sample in a different LUT cell).  natural: mirror-tiled
+    crops of the reference's golden Set5 results (tests/golden/set5_x4.npz) - smooth regions, edges,
+    a natural value histogram (SURVEY.md 8d asks for this set to be reported separately)."""
+    rng = np.random.default_rng(seed)
+    if DATA == "uniform":
+        return rng.integers(0, 256, (n, H, W, C), dtype=np.uint8)
+    d = np.load(os.path.join(ROOT, "tests", "golden", "set5_x4.npz"))
+    srcs = [d[k] for k in d.files if k.startswith("sr_")]
+    out = np.empty((n, H, W, C), np.uint8)
+    for i in range(n):
+        img = srcs[(i + seed) % len(srcs)]
+        img = np.concatenate([img, img[::-1]], 0)
+        img = np.concatenate([img, img[:, ::-1]], 1)           # mirror tile: seamless when repeated
+        oy, ox = rng.integers(0, img.shape[0]), rng.integers(0, img.shape[1])
+        ys = (np.arange(H) + oy) % img.shape[0]
+        xs = (np.arange(W) + ox) % img.shape[1]
+        out[i] = img[ys][:, xs]
+    return out
 
 
 class ClockSampler:
@@ -205,10 +225,14 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: per config, 16 for cfg2)")
     ap.add_argument("--config", type=str, default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--kernel", type=str, default="auto", choices=["auto", "generic", "tiled", "quad", "cell", "binned"])
+    ap.add_argument("--data", type=str, default="uniform", choices=["uniform", "natural"],
+                    help="synthetic frame content: i.i.d. uniform bytes (default, worst case) or tiled natural crops")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global DATA
+    DATA = args.data
     default_frames = select_config(args.config)
     if args.frames <= 0:
         args.frames = default_frames
@@ -383,7 +407,8 @@ def main():
     line = {
         "metric": "output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic" if DATA == "uniform" else "synthetic (mirror-tiled natural crops)",
         "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "kernel": args.kernel,
                    "l2": "per-step working set per GPU = {:.0f} MB in + {:.0f} MB out (> 126 MB L2), no flush".format(
                        F * H * W * C / 1e6, F * H * W * C * SCALE * SCALE / 1e6),

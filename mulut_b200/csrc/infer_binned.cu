@@ -272,6 +272,7 @@ __device__ __forceinline__ void binned_mode(const uint8_t *__restrict__ sp, uint
         const uint32_t t2 = sp[bn_tap_off(MODE, r, 2, true) * P + bn_tap_off(MODE, r, 2, false) * CT];
         const uint32_t t3 = sp[bn_tap_off(MODE, r, 3, true) * P + bn_tap_off(MODE, r, 3, false) * CT];
         const uint32_t v0 = (t1 >> 4) * SB + (t2 >> 4) * SC + (t3 >> 4) * SD;
+        // (forcing these through mad.lo to unload the ALU pipe measured 4 % slower: ptxas loses the shared shifts)
         uint32_t k0 = k0c, k1 = (t1 << 28) | SB, k2 = (t2 << 28) | SC, k3 = (t3 << 28) | SD;
         sort4_desc(k0, k1, k2, k3);
         const uint32_t f1 = k0 >> 28, f2 = k1 >> 28, f3 = k2 >> 28, f4 = k3 >> 28;
@@ -529,12 +530,9 @@ bool binned_supported(const StageArgs &a, int up)
 template <int CT>
 static int launch_binned_t(const BinnedArgs &b, const CUtensorMap &tmap, int num_sms, cudaStream_t stream)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
-        MULUT_CUDA(cudaFuncSetAttribute(stage_last2_binned_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)BN_SMEM));
-        attr_done = true;
-    }
+    // per device and cheap: set on every launch (one process may own several devices)
+    MULUT_CUDA(cudaFuncSetAttribute(stage_last2_binned_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)BN_SMEM));
     stage_last2_binned_kernel<CT><<<num_sms, BN_THREADS, BN_SMEM, stream>>>(b, tmap);
     MULUT_CUDA(cudaGetLastError());
     return MULUT_OK;

@@ -194,14 +194,12 @@ bool stage1_tma_supported(const StageArgs &a, int up)
 template <int CT>
 static int launch_stage1_t(Stage1Args &s, const CUtensorMap &tmap, int num_sms, long long n_tiles, cudaStream_t stream)
 {
-    static int per_sm = 0;
-    if (!per_sm) {
-        MULUT_CUDA(cudaFuncSetAttribute(stage_smem_tma_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)G1_SMEM));
-        int v = 0;
-        MULUT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, stage_smem_tma_kernel<CT>, G1_THREADS, G1_SMEM));
-        per_sm = v < 1 ? 1 : v;
-    }
+    // per device and cheap: set on every launch (one process may own several devices)
+    MULUT_CUDA(cudaFuncSetAttribute(stage_smem_tma_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)G1_SMEM));
+    int per_sm = 0;
+    MULUT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_smem_tma_kernel<CT>, G1_THREADS, G1_SMEM));
+    if (per_sm < 1) per_sm = 1;
     int ctas_per_mode = per_sm * num_sms / s.n_modes;
     if (ctas_per_mode < 1) ctas_per_mode = 1;
     if (ctas_per_mode > n_tiles) ctas_per_mode = (int)n_tiles;

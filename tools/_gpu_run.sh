@@ -1,7 +1,10 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_finetune.py -x -q -m gpu > gpurun_out/pytest_ft.log 2>&1; echo "pytest rc=$?"
-tail -5 gpurun_out/pytest_ft.log
-timeout 300 python tools/finetune_bench.py > gpurun_out/finetune_graph.json 2>gpurun_out/ft.err; cat gpurun_out/finetune_graph.json
-timeout 300 python tools/finetune_bench.py --smooth > gpurun_out/finetune_graph_smooth.json 2>gpurun_out/ft.err; cat gpurun_out/finetune_graph_smooth.json
-timeout 300 python tools/finetune_bench.py --eager > gpurun_out/finetune_eager.json 2>gpurun_out/ft.err; cat gpurun_out/finetune_eager.json
+for cfg in cfg2 x2s1 cfg3; do for k in auto quad; do
+timeout 300 python bench.py --config $cfg --data natural --kernel $k --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_nat_${cfg}_$k.json 2> gpurun_out/bench_auto.err; echo "bench rc=$?"
+python - <<PY
+import json
+d=json.load(open('gpurun_out/bench_nat_${cfg}_$k.json'))
+print('$cfg $k natural', round(d['value']), round(d['e2e']['value']), {k:round(v['ms_per_launch'],3) for k,v in d['kernels'].items()})
+PY
+done; done
