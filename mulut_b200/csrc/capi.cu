@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include "binned.cuh"
 #include "common.cuh"
 #include "infer.cuh"
 
@@ -116,6 +117,7 @@ static int run_stages(mulut_handle_s *h, Workspace &w, const uint8_t *d_in, uint
     if (rc) return rc;
 
     const uint8_t *cur = d_in;
+    bool planned = false;                      // the previous stage's K1b left K1f's histogram + plan in w.bn_ctl
     for (int s = 0; s < h->stages; ++s) {
         const bool last = s + 1 == h->stages;
         const int up = last ? h->scale : 1;
@@ -137,20 +139,33 @@ static int run_stages(mulut_handle_s *h, Workspace &w, const uint8_t *d_in, uint
         int done = 1;
         // K1f (binned, shared-memory slabs) when forced, or on AUTO for launches big enough to
         // amortise one 177 KB LUT load per SM; it falls through to K1c when TMA cannot map the frames.
-        if (uses_tiled(h, up, C) && binned_supported(a, up) &&
-            (h->kernel == MULUT_KERNEL_TILED_BINNED || (h->kernel == MULUT_KERNEL_AUTO && samples >= (1u << 20)))) {
+        const bool bin_policy = h->kernel == MULUT_KERNEL_TILED_BINNED ||
+                                (h->kernel == MULUT_KERNEL_AUTO && samples >= (1u << 20));
+        if (uses_tiled(h, up, C) && binned_supported(a, up) && bin_policy) {
             int launches = 0;
-            done = launch_stage_binned(a, w.bn_ctl, w.bn_list, w.bn_list_cap, stream, &launches, &h->prof);
+            done = launch_stage_binned(a, w.bn_ctl, w.bn_list, w.bn_list_cap, planned, stream, &launches, &h->prof);
             if (done < 0) return done;
             h->launches += launches;
         }
+        planned = false;
         if (done == 1 && uses_tiled(h, up, C)) {
             int launches = 0;
             // K1c (quad-cooperative) is the default: measured 6.83 ms vs 7.73 ms for K1d on
             // 16 x 1080p (profiles/r01_bench_quad_vs_cell.txt); K1d only on request.
             const bool owner_only = h->kernel == MULUT_KERNEL_TILED_CELL;
-            done = launch_stage_tiled_ws(a, up, w.partial, stream, &launches, &h->prof, owner_only);
+            // if the NEXT stage is the last one and will run K1f on this stage's output, K1b also
+            // produces K1f's histogram and plan (no extra launches)
+            BinPlanArgs pa;
+            memset(&pa, 0, sizeof pa);
+            if (up == 1 && s + 2 == h->stages && bin_policy && w.bn_ctl) {
+                StageArgs nx = a;
+                nx.in = a.out; nx.last = 1;
+                for (int m = 0; m < h->n_modes; ++m) nx.lut_slab[m] = h->lut_slab[m];
+                if (binned_supported(nx, h->scale)) pa = binned_plan_args(nx, w.bn_ctl, w.bn_list, w.bn_list_cap);
+            }
+            done = launch_stage_tiled_ws(a, up, w.partial, stream, &launches, &h->prof, owner_only, &pa);
             if (done < 0) return done;
+            planned = done == 0 && pa.ctl != nullptr && up == 1;
             h->launches += launches;
         }
         if (done == 1) {

@@ -54,8 +54,9 @@ int launch_stage_generic(const StageArgs &a, int up, cudaStream_t stream);
 // +1 when the configuration is not covered (caller falls back to generic).
 // partial: workspace of n_modes * N*H*W*C int16 (used when up == 1).
 // owner_only selects K1d (one lane per sample) over K1c (quad-cooperative) for the up = 2 last stage.
+struct BinPlanArgs;   // binned.cuh
 int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStream_t stream, int *launches,
-                          Prof *prof, bool owner_only);
+                          Prof *prof, bool owner_only, const BinPlanArgs *plan = nullptr);
 bool tiled_supported(int up, int interval, int n_modes);
 
 // K1g, the TMA-fed shared-memory kernel for up = 1 stages (infer_stage1.cu); same int16 partial
@@ -68,9 +69,11 @@ int launch_stage1_tma(const StageArgs &a, int16_t *partial, cudaStream_t stream)
 // launch_stage_binned returns MULUT_OK, an error (< 0) or +1 (not applicable: caller falls back).
 // ctl: binned_ctl_bytes() of device workspace; list: list_cap uint32 entries (orphan samples), may be null.
 bool binned_supported(const StageArgs &a, int up);
-int launch_stage_binned(const StageArgs &a, void *ctl, uint32_t *list, size_t list_cap, cudaStream_t stream,
-                        int *launches, Prof *prof);
+// planned: the control block already holds histogram + plan of a.in (K1b made them: binned_plan_args).
+int launch_stage_binned(const StageArgs &a, void *ctl, uint32_t *list, size_t list_cap, bool planned,
+                        cudaStream_t stream, int *launches, Prof *prof);
 size_t binned_ctl_bytes();
+struct BinPlanArgs binned_plan_args(const StageArgs &next_stage, void *ctl, const uint32_t *list, size_t list_cap);
 size_t slab_major_bytes();
 int build_slab_major(const int8_t *d_lut_vertex_major, uint8_t *d_slabs, cudaStream_t stream);
 

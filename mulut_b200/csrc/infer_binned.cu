@@ -33,14 +33,13 @@
 // Arithmetic follows SURVEY.md 8-SPEC (sr/4_test_lut.py:14-237, :279-306).
 #include <stdlib.h>
 
+#include "binned.cuh"
 #include "common.cuh"
 #include "infer.cuh"
 #include "tma.cuh"
 
 namespace mulut {
 
-constexpr int BN_TW = 96;                       // tile width, byte columns (multiple of C for C <= 4)
-constexpr int BN_TH = 32;                       // tile rows
 constexpr int BN_HX = 16;                       // box column of the tile's first sample: TMA needs the box to
                                                 // start on a 16-byte boundary, so the left halo (2*C <= 16 B)
                                                 // is fetched as a whole 16-byte granule
@@ -57,7 +56,6 @@ constexpr int BN_SLAB_WORDS = 4916;             // 17^3 = 4913 rows, padded so a
 constexpr int BN_SLAB_BYTES = BN_SLAB_WORDS * 4;
 constexpr int BN_BIN_BYTES = 3 * BN_SLAB_BYTES; // slabs 2b, 2b+1, 2b+2 of one mode
 constexpr int BN_MAX_MODES = 3;
-constexpr int BN_BINS = 8;
 constexpr size_t BN_SMEM = (size_t)BN_RING * BN_SLOT + BN_QCAP * 2 + (size_t)BN_MAX_MODES * BN_BIN_BYTES;
 
 static_assert(BN_TW / 4 * BN_TH == BN_SCAN_THREADS && BN_SCAN_THREADS % 32 == 0 && BN_SCAN_THREADS <= BN_THREADS,
@@ -89,116 +87,40 @@ int build_slab_major(const int8_t *d_lut, uint8_t *d_slabs, cudaStream_t stream)
 // control block (device, 256 B, zeroed before every launch) and the three small
 // kernels that prepare a launch: histogram -> plan -> orphan list
 // ---------------------------------------------------------------------------
-struct BinCtl {
-    unsigned long long hist[BN_BINS];   // samples per bin (sample >> 5)
-    int g[BN_BINS];                     // CTAs dealt to each bin; 0 = bin not resident
-    uint32_t orphan_mask;               // bins left to the L2-gather list kernel
-    uint32_t list_count;                // orphan samples collected
-};
-static_assert(sizeof(BinCtl) <= 256, "control block");
 size_t binned_ctl_bytes() { return 256; }
 
+// Stand-alone histogram + plan, for a stage whose input is not produced by K1b (single-stage models).
 __global__ void __launch_bounds__(256)
-bin_hist_kernel(const uint8_t *__restrict__ img, size_t total, BinCtl *__restrict__ ctl)
+bin_hist_kernel(const uint8_t *__restrict__ img, size_t total, BinPlanArgs pa)
 {
-    unsigned long long *__restrict__ hist = ctl->hist;
-    uint32_t cnt[BN_BINS];
-#pragma unroll
-    for (int b = 0; b < BN_BINS; ++b) cnt[b] = 0;
+    __shared__ uint32_t s_hist[BN_BINS];
+    if (threadIdx.x < BN_BINS) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    BinCounter bc;
     const size_t n16 = total / 16;
     const uint4 *__restrict__ v = reinterpret_cast<const uint4 *>(img);
-    unsigned long long packed = 0;
-    int pending = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
         const uint4 q = __ldg(v + i);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) packed += 1ull << (((w[k] >> (8 * e + 5)) & 7u) * 8);
-        if (++pending == 15) {                 // 240 samples: no 8-bit field can overflow
-#pragma unroll
-            for (int b = 0; b < BN_BINS; ++b) cnt[b] += (uint32_t)(packed >> (8 * b)) & 0xFFu;
-            packed = 0;
-            pending = 0;
-        }
+        bc.add_word(q.x); bc.add_word(q.y); bc.add_word(q.z); bc.add_word(q.w);
     }
-#pragma unroll
-    for (int b = 0; b < BN_BINS; ++b) cnt[b] += (uint32_t)(packed >> (8 * b)) & 0xFFu;
     if (blockIdx.x == 0 && threadIdx.x == 0)
-        for (size_t i = n16 * 16; i < total; ++i) {
-            const uint32_t bb = img[i] >> 5;
-#pragma unroll
-            for (int b = 0; b < BN_BINS; ++b) cnt[b] += (bb == (uint32_t)b);
-        }
-#pragma unroll
-    for (int b = 0; b < BN_BINS; ++b) {
-        uint32_t c = cnt[b];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if ((threadIdx.x & 31) == 0 && c) atomicAdd(hist + b, (unsigned long long)c);
+        for (size_t i = n16 * 16; i < total; ++i) bc.add_byte(img[i]);
+    bc.reduce_into(s_hist);
+    __syncthreads();
+    if (threadIdx.x < BN_BINS && s_hist[threadIdx.x]) atomicAdd(&pa.ctl->hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&pa.ctl->ticket, 1u) == gridDim.x - 1) {      // last block: plan
+        __threadfence();
+        bin_plan(pa.ctl, pa.n_tiles, pa.G, pa.list_cap, pa.allow_orphans);
     }
 }
 
-// Plan (one thread): which bins get shared-memory CTAs, how many, and which are "orphans".
-// A bin is worth a resident CTA group only if its samples outweigh the fixed cost of
-// walking every tile once more (scan + barriers); sparse bins go to a list that the
-// generic L2-gather kernel finishes (stage_generic_list_kernel).  Costs in SM cycles.
-constexpr unsigned long long BN_CV = 1200;      // per tile visit of one CTA (tools/bn_timing.py: 1140-1200)
-constexpr unsigned long long BN_CS = 11;        // per sample interpolated from shared memory (measured 10.7-14.4)
-constexpr unsigned long long BN_CG = 26;        // per sample interpolated by the list kernel
-__global__ void bin_plan_kernel(BinCtl *__restrict__ ctl, long long n_tiles, int G, unsigned long long list_cap,
-                                int allow_orphans)
+// Orphan list: linear indices of the samples whose bin has no resident CTAs.  Every CTA of K1f scans
+// its slice of the stage input before it starts on its tiles (the scan overlaps the LUT bulk copies).
+__device__ __forceinline__ void collect_orphans(const uint8_t *__restrict__ img, size_t total, uint32_t mask,
+                                                uint32_t *__restrict__ count, uint32_t *__restrict__ list)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    unsigned long long n[BN_BINS], cost[BN_BINS], total = 0, orph = 0;
-    bool res[BN_BINS];
-    for (int b = 0; b < BN_BINS; ++b) {
-        n[b] = ctl->hist[b];
-        res[b] = n[b] > 0 && (!allow_orphans || n[b] * (BN_CG - BN_CS) > (unsigned long long)n_tiles * BN_CV);
-        if (n[b] && !res[b]) orph += n[b];
-    }
-    while (orph > list_cap) {                               // the list is bounded: promote the largest orphan bin
-        int best = -1;
-        for (int b = 0; b < BN_BINS; ++b)
-            if (n[b] && !res[b] && (best < 0 || n[b] > n[best])) best = b;
-        res[best] = true;
-        orph -= n[best];
-    }
-    uint32_t mask = 0;
-    for (int b = 0; b < BN_BINS; ++b) {
-        cost[b] = res[b] ? (unsigned long long)n_tiles * BN_CV + n[b] * BN_CS : 0ull;
-        total += cost[b];
-        if (n[b] && !res[b]) mask |= 1u << b;
-    }
-    int g[BN_BINS], used = 0;
-    for (int b = 0; b < BN_BINS; ++b) {
-        g[b] = cost[b] ? max(1, (int)(cost[b] * (unsigned long long)G / total)) : 0;
-        used += g[b];
-    }
-    while (total && used < G) {                             // hand the rest to the most loaded groups
-        int best = -1;
-        for (int b = 0; b < BN_BINS; ++b)
-            if (g[b] && (best < 0 || cost[b] * g[best] > cost[best] * g[b])) best = b;
-        ++g[best]; ++used;
-    }
-    while (used > G) {
-        int best = -1;
-        for (int b = 0; b < BN_BINS; ++b)
-            if (g[b] > 1 && (best < 0 || cost[b] * g[best] < cost[best] * g[b])) best = b;
-        if (best < 0) break;
-        --g[best]; --used;
-    }
-    for (int b = 0; b < BN_BINS; ++b) ctl->g[b] = g[b];
-    ctl->orphan_mask = mask;
-}
-
-// Orphan list: linear indices of the samples whose bin has no resident CTAs.
-__global__ void __launch_bounds__(256)
-bin_collect_kernel(const uint8_t *__restrict__ img, size_t total, BinCtl *__restrict__ ctl, uint32_t *__restrict__ list)
-{
-    const uint32_t mask = ctl->orphan_mask;
-    if (!mask) return;
     const size_t n16 = total / 16;
     const uint4 *__restrict__ v = reinterpret_cast<const uint4 *>(img);
     const int lane = threadIdx.x & 31;
@@ -231,7 +153,7 @@ bin_collect_kernel(const uint8_t *__restrict__ img, size_t total, BinCtl *__rest
                 if (lane >= o) incl += t;
             }
             uint32_t base = 0;
-            if (lane == 31) base = atomicAdd(&ctl->list_count, incl);
+            if (lane == 31) base = atomicAdd(count, incl);
             base = __shfl_sync(0xffffffffu, base, 31);
             uint32_t pos = base + incl - cnt;
             while (hits) {
@@ -243,7 +165,7 @@ bin_collect_kernel(const uint8_t *__restrict__ img, size_t total, BinCtl *__rest
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         for (size_t i = n16 * 16; i < total; ++i)
-            if ((mask >> (img[i] >> 5)) & 1u) list[atomicAdd(&ctl->list_count, 1u)] = (uint32_t)i;
+            if ((mask >> (img[i] >> 5)) & 1u) list[atomicAdd(count, 1u)] = (uint32_t)i;
 }
 
 // ---------------------------------------------------------------------------
@@ -297,7 +219,10 @@ struct BinnedArgs {
     int n_modes;
     char modes[BN_MAX_MODES + 1];
     const uint8_t *slabs[BN_MAX_MODES];      // slab-major biased tables
-    const BinCtl *ctl;                       // plan: CTAs per bin
+    BinCtl *ctl;                             // plan: CTAs per bin, orphan mask and counter
+    const uint8_t *in;                       // the stage input (orphan scan) and its size in samples
+    size_t total;
+    uint32_t *list;                          // orphan list, or null
 };
 
 // Optional phase timing (build with -DMULUT_BN_TIMING): thread 0 of every CTA accumulates
@@ -349,7 +274,11 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
     }
     __syncthreads();
     const int bin = s_alloc[0], me = s_alloc[1], gb = s_alloc[2];
-    if (bin >= BN_BINS || me >= n_tiles) return;
+    const bool idle = bin >= BN_BINS || me >= n_tiles;
+    if (idle) {                                            // no tiles for this CTA: it still scans its slice for orphans
+        if (a.list && a.ctl->orphan_mask) collect_orphans(a.in, a.total, a.ctl->orphan_mask, &a.ctl->list_count, a.list);
+        return;
+    }
     const int n_my = (int)((n_tiles - me + gb - 1) / gb);
 
     auto issue = [&](int i) {                              // thread 0 only: TMA load of my i-th tile
@@ -374,6 +303,8 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
             bulk_g2s(smem_u32(s_lut + m * BN_BIN_BYTES), a.slabs[m] + (size_t)bin * 2 * BN_SLAB_BYTES, BN_BIN_BYTES, lb);
         for (int i = 0; i < BN_AHEAD && i < n_my; ++i) issue(i);
     }
+    // orphan scan of my slice of the input while the LUT slabs and the first tiles are in flight
+    if (a.list && a.ctl->orphan_mask) collect_orphans(a.in, a.total, a.ctl->orphan_mask, &a.ctl->list_count, a.list);
 
     // scan mapping: the tile's TW x TH samples are TW/4 x TH = BN_THREADS words, one per thread
     const int srow = tid / (BN_TW / 4), swc = tid - srow * (BN_TW / 4);
@@ -540,45 +471,63 @@ static int launch_binned_t(const BinnedArgs &b, const CUtensorMap &tmap, int num
 
 int launch_stage_generic_list2(const StageArgs &a, const uint32_t *list, const uint32_t *count, cudaStream_t stream);
 
-// ctl: binned_ctl_bytes() of device workspace; list: list_cap uint32 entries of device workspace
-int launch_stage_binned(const StageArgs &a, void *ctl_mem, uint32_t *list, size_t list_cap, cudaStream_t stream,
-                        int *launches, Prof *prof)
+static int binned_allow_orphans(const uint32_t *list, size_t total)
+{
+    const char *env = getenv("MULUT_BN_ORPHANS");
+    return (!env || env[0] != '0') && list && total < 0xFFFFFFFFull;
+}
+
+// What K1b needs to produce the histogram + plan of the NEXT stage's input (N,H,W,C as this stage's).
+BinPlanArgs binned_plan_args(const StageArgs &a, void *ctl_mem, const uint32_t *list, size_t list_cap)
+{
+    BinPlanArgs pa;
+    const int WC = a.W * a.C;
+    pa.ctl = static_cast<BinCtl *>(ctl_mem);
+    pa.n_tiles = (long long)a.N * ((a.H + BN_TH - 1) / BN_TH) * ((WC + BN_TW - 1) / BN_TW);
+    pa.G = a.num_sms;
+    pa.list_cap = (unsigned long long)list_cap;
+    pa.allow_orphans = binned_allow_orphans(list, (size_t)a.N * a.H * WC);
+    return pa;
+}
+
+// ctl: binned_ctl_bytes() of device workspace; list: list_cap uint32 entries of device workspace.
+// planned: the control block already holds the histogram + plan of a.in (K1b produced them).
+int launch_stage_binned(const StageArgs &a, void *ctl_mem, uint32_t *list, size_t list_cap, bool planned,
+                        cudaStream_t stream, int *launches, Prof *prof)
 {
     const size_t total = (size_t)a.N * a.H * a.W * a.C;
     if (total == 0) return MULUT_OK;
     CUtensorMap tmap;
     if (tma_encode_frames(&tmap, a.in, a.N, a.H, a.W * a.C, BN_BOXW, BN_BOXH) != 0) return 1;   // caller falls back
     BinCtl *ctl = static_cast<BinCtl *>(ctl_mem);
+    const BinPlanArgs pa = binned_plan_args(a, ctl_mem, list, list_cap);
     BinnedArgs b;
     memset(&b, 0, sizeof b);
     b.out = a.out; b.N = a.N; b.H = a.H; b.W = a.W; b.C = a.C; b.n_modes = a.n_modes; b.ctl = ctl;
+    b.in = a.in; b.total = total; b.list = pa.allow_orphans ? list : nullptr;
     for (int m = 0; m < a.n_modes; ++m) { b.modes[m] = a.modes[m]; b.slabs[m] = a.lut_slab[m]; }
-    const int WC = a.W * a.C;
-    const long long n_tiles = (long long)a.N * ((a.H + BN_TH - 1) / BN_TH) * ((WC + BN_TW - 1) / BN_TW);
-    const char *env = getenv("MULUT_BN_ORPHANS");
-    const int allow_orphans = (!env || env[0] != '0') && list && total < 0xFFFFFFFFull;
 
-    prof->begin(MULUT_PROF_BIN_HIST, stream);
-    MULUT_CUDA(cudaMemsetAsync(ctl, 0, binned_ctl_bytes(), stream));
-    size_t blocks = (total / 16 + 255) / 256 + 1;
-    if (blocks > (size_t)a.num_sms * 8) blocks = (size_t)a.num_sms * 8;
-    bin_hist_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.in, total, ctl);
-    bin_plan_kernel<<<1, 32, 0, stream>>>(ctl, n_tiles, a.num_sms, (unsigned long long)list_cap, allow_orphans);
-    if (allow_orphans) bin_collect_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.in, total, ctl, list);
-    prof->end(stream);
-    MULUT_CUDA(cudaGetLastError());
-
+    if (!planned) {
+        prof->begin(MULUT_PROF_BIN_HIST, stream);
+        MULUT_CUDA(cudaMemsetAsync(ctl, 0, binned_ctl_bytes(), stream));
+        size_t blocks = (total / 16 + 255) / 256 + 1;
+        if (blocks > (size_t)a.num_sms * 8) blocks = (size_t)a.num_sms * 8;
+        bin_hist_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.in, total, pa);
+        prof->end(stream);
+        MULUT_CUDA(cudaGetLastError());
+        *launches += 1;
+    }
     prof->begin(MULUT_PROF_LAST_BINNED, stream);
     int rc = a.C == 3 ? launch_binned_t<3>(b, tmap, a.num_sms, stream) : launch_binned_t<1>(b, tmap, a.num_sms, stream);
     prof->end(stream);
     if (rc) return rc;
-    *launches += 3;
-    if (allow_orphans) {
+    *launches += 1;
+    if (pa.allow_orphans) {
         prof->begin(MULUT_PROF_BIN_ORPHANS, stream);
         rc = launch_stage_generic_list2(a, list, &ctl->list_count, stream);
         prof->end(stream);
         if (rc) return rc;
-        *launches += 2;
+        *launches += 1;
     }
     return MULUT_OK;
 }

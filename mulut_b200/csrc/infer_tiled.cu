@@ -25,6 +25,7 @@
 // Arithmetic follows SURVEY.md 8-SPEC (sr/4_test_lut.py:14-237, :279-306).
 #include <cuda/barrier>
 
+#include "binned.cuh"
 #include "common.cuh"
 #include "infer.cuh"
 
@@ -200,10 +201,13 @@ stage_smem_kernel(const __grid_constant__ StageArgs a, int16_t *__restrict__ par
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 combine_kernel(const int16_t *__restrict__ partial, uint8_t *__restrict__ out, size_t total,
-               int n_modes, int last)
+               int n_modes, int last, BinPlanArgs pa)
 {
     const uint32_t den = last ? 16u * n_modes : 64u * n_modes;
     const int bias = last ? 0 : 127 * (int)den;
+    // When the next stage is the binned kernel K1f, this kernel also counts the 8-bin histogram of
+    // the bytes it writes (pa.ctl != null) and its last block turns it into K1f's plan.
+    BinCounter bc;
     // 8 samples per thread when the planes allow 16-byte loads
     const bool vec = (total % 8 == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
     const size_t total8 = vec ? total / 8 : 0;
@@ -226,13 +230,31 @@ combine_kernel(const int16_t *__restrict__ partial, uint8_t *__restrict__ out, s
             hi |= rhe_div_clamp_u8(s[4 + k] + bias, den) << (8 * k);
         }
         reinterpret_cast<uint2 *>(out)[i] = make_uint2(lo, hi);
+        if (pa.ctl) { bc.add_word(lo); bc.add_word(hi); }
     }
     if (total8 == 0) {
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
              i += (size_t)gridDim.x * blockDim.x) {
             int s = 0;
             for (int m = 0; m < n_modes; ++m) s += partial[(size_t)m * total + i];
-            out[i] = (uint8_t)rhe_div_clamp_u8(s + bias, den);
+            const uint32_t o = rhe_div_clamp_u8(s + bias, den);
+            out[i] = (uint8_t)o;
+            if (pa.ctl) bc.add_byte(o);
+        }
+    }
+    if (pa.ctl) {                                          // uniform: a kernel argument
+        __shared__ uint32_t s_hist[BN_BINS];
+        if (threadIdx.x < BN_BINS) s_hist[threadIdx.x] = 0;
+        __syncthreads();
+        bc.reduce_into(s_hist);
+        __syncthreads();
+        if (threadIdx.x < BN_BINS && s_hist[threadIdx.x])
+            atomicAdd(&pa.ctl->hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(&pa.ctl->ticket, 1u) == gridDim.x - 1) {   // last block: plan
+            __threadfence();
+            bin_plan(pa.ctl, pa.n_tiles, pa.G, pa.list_cap, pa.allow_orphans);
         }
     }
 }
@@ -844,7 +866,7 @@ static int launch_quad4_stage(const StageArgs &a, cudaStream_t stream)
 
 // partial: workspace of n_modes * N*H*W*C int16 (only used for up == 1)
 int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStream_t stream, int *launches,
-                          Prof *prof, bool owner_only)
+                          Prof *prof, bool owner_only, const BinPlanArgs *plan)
 {
     const size_t total = (size_t)a.N * a.H * a.W * a.C;
     if (total == 0) return MULUT_OK;
@@ -863,8 +885,14 @@ int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStre
         size_t blocks = (total / 8 + 255) / 256 + 1;
         const size_t cap = (size_t)a.num_sms * 16;
         if (blocks > cap) blocks = cap;
+        BinPlanArgs pa;
+        memset(&pa, 0, sizeof pa);
+        if (plan && plan->ctl) {                       // the next stage is K1f: histogram + plan ride on K1b
+            pa = *plan;
+            MULUT_CUDA(cudaMemsetAsync(pa.ctl, 0, sizeof(BinCtl), stream));
+        }
         prof->begin(MULUT_PROF_COMBINE, stream);
-        combine_kernel<<<(unsigned)blocks, 256, 0, stream>>>(partial, a.out, total, a.n_modes, a.last);
+        combine_kernel<<<(unsigned)blocks, 256, 0, stream>>>(partial, a.out, total, a.n_modes, a.last, pa);
         prof->end(stream);
         MULUT_CUDA(cudaGetLastError());
         *launches += 2;
