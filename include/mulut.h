@@ -170,6 +170,17 @@ int mulut_stage_bwd_f32(const float *const *d_weights, int n_modes, const char *
                         void *stream);
 
 /*
+ * The optimiser step of sr/3_finetune_lut.py:85-87,134 (torch.optim.Adam, betas/eps as given there, L2
+ * weight decay, no amsgrad) fused into one pass over flat buffers of n floats.
+ *   d_lr    device scalar: the learning rate of this step (LambdaLR value, :88-95)
+ *   d_step  device scalar float: step counter, incremented by the call (bias corrections use the new value)
+ * All pointers are device pointers; asynchronous on `stream`, capturable in a CUDA graph.
+ */
+int mulut_adam_step_f32(float *d_param, const float *d_grad, float *d_exp_avg, float *d_exp_avg_sq, size_t n,
+                        const float *d_lr, float beta1, float beta2, float eps, float weight_decay,
+                        float *d_step, void *stream);
+
+/*
  * On-device report metrics of eltr._worker, sr/4_test_lut.py:309-314: PSNR and SSIM on the BT.601
  * luma of two RGB uint8 frames, definitions of common/utils.py:42-101 (_rgb2ycbcr, PSNR with
  * shave_border, cal_ssim: 11x11 Gaussian window sigma 1.5, 'valid', float64).

@@ -54,9 +54,7 @@ class GraphedStep:
         self.model = model_G
         self.params = [p for p in model_G.parameters() if p.requires_grad]
         self.bucket = mdist.FlatGradBucket(self.params)
-        self.lr = torch.tensor(float(lr0), device=device)
-        self.opt = torch.optim.Adam(self.params, lr=self.lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=weight_decay,
-                                    capturable=True)
+        self.opt = mdist.FusedAdam(self.bucket, lr0, betas=(0.9, 0.999), eps=1e-8, weight_decay=weight_decay)
         self.im = torch.zeros(im_shape, device=device)
         self.lb = torch.zeros(lb_shape, device=device)
         saved = [p.detach().clone() for p in self.params]
@@ -70,10 +68,7 @@ class GraphedStep:
         with torch.no_grad():                    # roll the warm-up back: parameters and Adam state
             for p, q in zip(self.params, saved):
                 p.copy_(q)
-            for st in self.opt.state.values():
-                for v in st.values():
-                    if torch.is_tensor(v):
-                        v.zero_()
+            self.opt.reset_state()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._body()
@@ -89,7 +84,7 @@ class GraphedStep:
     def __call__(self, im, lb, lr: float):
         self.im.copy_(im)
         self.lb.copy_(lb)
-        self.lr.fill_(float(lr))
+        self.opt.set_lr(lr)
         self.graph.replay()
         return self.loss.clone()                  # device scalar (the graph's output buffer is reused); .item() synchronises
 

@@ -805,3 +805,52 @@ extern "C" int mulut_stage_bwd_f32(const float *const *d_weights, int n_modes, c
     MULUT_CUDA(cudaGetLastError());
     return MULUT_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Fused Adam over the flat LUT parameter buffer (sr/3_finetune_lut.py:85-87,134: torch.optim.Adam
+// with betas (0.9, 0.999), eps 1e-8, optional L2 weight decay, no amsgrad), one pass instead of the
+// ~10 foreach kernels of the stock optimizer.  The learning rate and the step counter live on the
+// device so the call can be captured in a CUDA graph and replayed with a new rate.
+//   g' = g + wd * p;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2
+//   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// ---------------------------------------------------------------------------
+namespace mulut {
+__global__ void __launch_bounds__(256)
+adam_step_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+                 size_t n, const float *__restrict__ d_lr, float b1, float b2, float eps, float wd,
+                 const float *__restrict__ d_step /* already incremented */)
+{
+    const float t = *d_step, lr = *d_lr;
+    const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = 1.f / sqrtf(bc2);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float pi = p[i];
+        const float gi = g[i] + wd * pi;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] = pi - step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+    }
+}
+__global__ void adam_tick_kernel(float *d_step) { *d_step += 1.f; }
+}  // namespace mulut
+
+extern "C" int mulut_adam_step_f32(float *d_param, const float *d_grad, float *d_exp_avg, float *d_exp_avg_sq, size_t n,
+                                   const float *d_lr, float beta1, float beta2, float eps, float weight_decay,
+                                   float *d_step, void *stream)
+{
+    if (!d_param || !d_grad || !d_exp_avg || !d_exp_avg_sq || !d_lr || !d_step) {
+        set_error("adam: null argument");
+        return MULUT_E_BAD_ARG;
+    }
+    if (n == 0) return MULUT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    adam_tick_kernel<<<1, 1, 0, st>>>(d_step);
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    adam_step_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, d_lr, beta1, beta2, eps,
+                                                       weight_decay, d_step);
+    MULUT_CUDA(cudaGetLastError());
+    return MULUT_OK;
+}

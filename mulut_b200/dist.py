@@ -84,3 +84,47 @@ class FlatGradBucket:
         if dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.div_(dist.get_world_size())
+
+
+class FusedAdam:
+    """torch.optim.Adam(params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay) of
+    3_finetune_lut.py:85-87 as ONE kernel over flat buffers (mulut_adam_step_f32): the parameters
+    are re-pointed at slices of one flat tensor (their values and names are unchanged), the
+    gradients are the FlatGradBucket's buffer, the two moment buffers are flat as well.  The
+    learning rate and the step counter are device scalars, so the step is CUDA-graph capturable."""
+
+    def __init__(self, bucket: "FlatGradBucket", lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0):
+        self.bucket, self.betas, self.eps, self.weight_decay = bucket, betas, float(eps), float(weight_decay)
+        ref = bucket.flat
+        if not ref.is_cuda:
+            raise RuntimeError("FusedAdam needs CUDA parameters (no CPU fallback)")
+        self.flat_param = torch.empty_like(ref)
+        off = 0
+        with torch.no_grad():
+            for p in bucket.params:
+                n = p.numel()
+                self.flat_param[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat_param[off:off + n].view_as(p)
+                off += n
+        self.exp_avg = torch.zeros_like(ref)
+        self.exp_avg_sq = torch.zeros_like(ref)
+        self.lr = torch.tensor(float(lr), device=ref.device)
+        self.step_count = torch.zeros((), device=ref.device)
+
+    def set_lr(self, lr: float) -> None:
+        self.lr.fill_(float(lr))
+
+    def step(self) -> None:
+        import ctypes
+        from . import _lib
+        dev = self.flat_param.device
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().mulut_adam_step_f32(
+                self.flat_param.data_ptr(), self.bucket.flat.data_ptr(), self.exp_avg.data_ptr(),
+                self.exp_avg_sq.data_ptr(), self.flat_param.numel(), self.lr.data_ptr(), self.betas[0], self.betas[1],
+                self.eps, self.weight_decay, self.step_count.data_ptr(), stream))
+
+    def reset_state(self) -> None:
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.step_count.zero_()
