@@ -255,9 +255,19 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: ONE JSON line
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the communicator comes up: park stdout on
+        # stderr until then so that rank 0's stdout carries ONE JSON line and nothing else
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     kernel = {"auto": _lib.KERNEL_AUTO, "generic": _lib.KERNEL_GENERIC, "tiled": _lib.KERNEL_TILED,
               "quad": _lib.KERNEL_TILED_QUAD, "cell": _lib.KERNEL_TILED_CELL,

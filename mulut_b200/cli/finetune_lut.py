@@ -151,6 +151,14 @@ def main(argv=None):
                                                           (time.time() - st) / max(1, opt.totalIter)))
         model_G.export_luts(opt.expDir)
         print("Finetuned LUT saved to {}".format(opt.expDir))
+    if world > 1:
+        # communicators captured in a CUDA graph can hang in their destructor: leave without tearing them down
+        import os
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -113,6 +113,8 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         dt = e0.elapsed_time(e1) * 1e-3 / args.steps
+        loss = loss.clone()
+        del gs                                   # drop the captured graph (it holds NCCL work) before the group goes away
     t = torch.tensor([dt], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -143,7 +145,11 @@ def main():
     if rank == 0:
         print(json.dumps(res), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)          # NCCL communicators that were captured in a CUDA graph can hang in their destructor
 
 
 if __name__ == "__main__":
