@@ -133,3 +133,26 @@ def test_auto_picks_binned_for_large_launches_and_host_path_agrees():
         assert "last_binned" in prof, prof
         assert (out == ref).all(), int((out != ref).sum())
         assert (eng(frames) == ref).all()          # host path: one frame per launch
+
+
+@pytest.mark.parametrize("scale,stages,modes,shape", [(1, 2, "sdy", (2, 70, 112, 3)), (1, 3, "ds", (1, 33, 96, 1)),
+                                                      (4, 2, "sdy", (2, 45, 80, 3)), (3, 2, "ys", (1, 64, 160, 3)),
+                                                      (1, 1, "y", (1, 2, 16, 3))])
+def test_tma_stage_kernel_k1g(scale, stages, modes, shape):
+    """K1g (TMA tile ring + shared-memory LUT) serves every up = 1 stage of TMA-mappable frames,
+    whatever the last stage is: scales 1/3/4 pair it with K1b-as-last-stage, K0 or K1e."""
+    import torch
+    from mulut_b200.infer import LutEngine
+    rng = np.random.default_rng(sum(shape) + scale)
+    luts = O.random_luts(50 + scale, stages, modes, scale)
+    frames = rng.integers(0, 256, shape, dtype=np.uint8)
+    ref = CO.sr_u8(frames, luts, stages, modes, scale)
+    with LutEngine(luts, stages, modes, scale, 4, device=0) as eng:          # AUTO
+        eng.profile(True)
+        out = eng(torch.from_numpy(frames).cuda()).cpu().numpy()
+        prof = eng.profile_read()
+    if stages > 1 or scale == 1:
+        assert "smem_stage" in prof, prof
+    assert (out == ref).all(), (scale, stages, modes, int((out != ref).sum()))
+    with LutEngine(luts, stages, modes, scale, 4, device=0, kernel=1) as eng:  # K1a (no TMA) gives the same bytes
+        assert (eng(torch.from_numpy(frames).cuda()).cpu().numpy() == ref).all()
