@@ -402,6 +402,17 @@ def main():
                     "shape from a table of the same kind, all SMs".format(peak_variant),
         "frac": ach_gathers / pk if pk else None,
         "whole_step_Ggathers_per_s": samples_per_step * 120 * args.steps / (ms * 1e-3) / 1e9 if STAGES == 2 else None,
+        # the north star's own yardstick: the L2 gather roofline.  The shared-memory kernels are not bound by it -
+        # the whole step delivers more vertex rows per second than L2 can serve with its best fetch shape
+        # (one 64-byte cell = the 5 vertices of an interpolation) or with plain 4-byte gathers.
+        "whole_step_vs_l2_gather_roofline": {
+            "l2_cell64_x5_Ggathers_per_s": (peak_gathers("quad_cell64") or 0) / 1e9,
+            "l2_u32_Ggathers_per_s": (peak_gathers("ldg_u32") or 0) / 1e9,
+            "frac_of_l2_cell64": (samples_per_step * 60 * STAGES * args.steps / (ms * 1e-3)) / peak_gathers("quad_cell64")
+            if peak_gathers("quad_cell64") else None,
+            "frac_of_l2_u32": (samples_per_step * 60 * STAGES * args.steps / (ms * 1e-3)) / peak_gathers("ldg_u32")
+            if peak_gathers("ldg_u32") else None,
+        },
         "per_kernel": per_kernel,
         "microbench": gp,
     }
