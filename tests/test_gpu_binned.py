@@ -156,3 +156,52 @@ def test_tma_stage_kernel_k1g(scale, stages, modes, shape):
     assert (out == ref).all(), (scale, stages, modes, int((out != ref).sum()))
     with LutEngine(luts, stages, modes, scale, 4, device=0, kernel=1) as eng:  # K1a (no TMA) gives the same bytes
         assert (eng(torch.from_numpy(frames).cuda()).cpu().numpy() == ref).all()
+
+
+def test_binned_sparse_resident_bins_walk_many_tiles(monkeypatch):
+    """With orphaning off, a bin holding 0.5 % of the samples still gets CTAs of its own: each walks
+    hundreds of tiles, wraps the TMA ring many times and lives on carried queue entries and forced
+    partial rounds - the paths a dense bin never takes."""
+    import torch
+    from mulut_b200.infer import LutEngine
+    monkeypatch.setenv("MULUT_BN_ORPHANS", "0")
+    rng = np.random.default_rng(21)
+    img = rng.integers(100, 156, (2, 540, 960, 3))
+    sel = rng.random(img.shape) < 0.02
+    img[sel] = rng.integers(0, 256, int(sel.sum()))
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    luts = O.random_luts(17, 1, "sdy", 2)
+    ref = CO.sr_u8(img, luts, 1, "sdy", 2)
+    with LutEngine(luts, 1, "sdy", 2, 4, device=0, kernel=3) as eng:
+        out = _run(eng, img)
+    assert (out == ref).all(), int((out != ref).sum())
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_binned_randomised_shapes_and_distributions(seed, monkeypatch):
+    """Seeded fuzz: random TMA-mappable shapes, batch sizes, channel counts, stage counts and value
+    distributions (uniform, narrow band, bimodal, heavy tails), with and without orphaning."""
+    from mulut_b200.infer import LutEngine
+    rng = np.random.default_rng(1000 + seed)
+    C = int(rng.choice([1, 3]))
+    W = int(rng.integers(1, 20)) * 16
+    H = int(rng.integers(1, 150))
+    N = int(rng.integers(1, 4))
+    stages = int(rng.integers(1, 3))
+    monkeypatch.setenv("MULUT_BN_ORPHANS", str(seed % 2))
+    kind = seed % 4
+    if kind == 0:
+        img = rng.integers(0, 256, (N, H, W, C))
+    elif kind == 1:
+        lo = int(rng.integers(0, 200))
+        img = rng.integers(lo, lo + int(rng.integers(2, 56)), (N, H, W, C))
+    elif kind == 2:
+        img = np.where(rng.random((N, H, W, C)) < 0.5, rng.integers(0, 64, (N, H, W, C)), rng.integers(192, 256, (N, H, W, C)))
+    else:
+        img = np.clip(rng.normal(128, 20, (N, H, W, C)) + (rng.random((N, H, W, C)) < 0.01) * rng.normal(0, 120, (N, H, W, C)), 0, 255)
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    luts = O.random_luts(300 + seed, stages, "sdy", 2)
+    ref = CO.sr_u8(img, luts, stages, "sdy", 2)
+    with LutEngine(luts, stages, "sdy", 2, 4, device=0, kernel=3) as eng:
+        out = _run(eng, img)
+    assert (out == ref).all(), (seed, img.shape, stages, int((out != ref).sum()))
