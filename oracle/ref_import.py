@@ -54,6 +54,11 @@ def model_module():
     return _load("ref_sr_model", os.path.join(REF_ROOT, "sr", "model.py"))
 
 
+def transfer_module():
+    """sr/2_transfer_to_lut.py (the LUT producer; only its grid-enumeration helpers are used)."""
+    return _load("ref_2_transfer_to_lut", os.path.join(REF_ROOT, "sr", "2_transfer_to_lut.py"))
+
+
 def ref_pipeline(img_u8, luts, stages, modes, scale, interval=4):
     """The reference's own stage/mode/rotation loop (4_test_lut.py:279-306)
     re-driven around the reference's FourSimplexInterpFaster.  ``luts`` maps

@@ -190,3 +190,42 @@ def test_metrics_known_values():
     assert modcrop(np.zeros((10, 11, 3)), 4).shape == (8, 8, 3)
     y = rgb2ycbcr(np.array([[[255, 255, 255], [0, 0, 0]]], dtype=np.uint8))[..., 0]
     assert np.allclose(y, [[235.0, 16.0]])
+
+
+def test_transfer_grid_enumeration_and_round_trip(tmp_path):
+    """2_transfer_to_lut.py's grid: row a*L^3+b*L^2+c*L+d is the patch [[a,b],[c,d]] with the last grid
+    point at 255; a 'network' that reads a table at the grid points reproduces the table (the
+    enumeration order is the retrieval kernels' row order), file names and int8 quantisation as the
+    reference writes them."""
+    from mulut_b200 import transfer as T
+    x = T.get_input_tensor(4)
+    L = 17
+    assert x.shape == (L ** 4, 1, 2, 2) and x.dtype == torch.float32
+    base = np.concatenate([np.arange(0, 256, 16), [255]])
+    for idx in (0, 1, 16, 17, 5000, 83520, 12345):
+        a, r = divmod(idx, L ** 3); b, r = divmod(r, L ** 2); c, d = divmod(r, L)
+        assert np.allclose(x[idx, 0].numpy() * 255.0, [[base[a], base[b]], [base[c], base[d]]]), idx
+    for mode, pos in (("d", ((0, 0), (0, 2), (2, 0), (2, 2))), ("y", ((0, 0), (1, 1), (1, 2), (2, 1)))):
+        xm = T.get_mode_input_tensor(x[:1000], mode)
+        assert xm.shape == (1000, 1, 3, 3)
+        for k, (yy, xx) in enumerate(pos):
+            assert torch.equal(xm[:, 0, yy, xx], x[:1000, 0, k // 2, k % 2])
+        assert float(xm.sum()) == pytest.approx(float(x[:1000].sum()))
+    with pytest.raises(ValueError, match="Mode e not implemented."):
+        T.get_mode_input_tensor(x[:4], "e")
+    # round trip through a table-reading "network"
+    rng = np.random.default_rng(0)
+    table = rng.integers(-127, 128, (L ** 4, 4)).astype(np.int8)
+
+    def net_fn(batch, stage, mode):
+        taps = batch.reshape(batch.shape[0], -1) * 255.0
+        taps = taps[:, [0, 1, 2, 3]] if mode == "s" else taps[:, [0, 2, 6, 8]]
+        gi = torch.where(taps >= 255, torch.tensor(16.0), taps / 16).round().long()
+        rows = ((gi[:, 0] * L + gi[:, 1]) * L + gi[:, 2]) * L + gi[:, 3]
+        return torch.from_numpy(table.astype(np.float32))[rows].reshape(-1, 1, 2, 2) / 127.0
+
+    out = T.transfer_to_lut(net_fn, 1, "sd", 2, 4, exp_dir=str(tmp_path))
+    for m in "sd":
+        assert out["s1_" + m].dtype == np.int8 and out["s1_" + m].shape == (L ** 4, 1, 2, 2)
+        assert (out["s1_" + m].reshape(-1, 4) == table).all()
+        assert (np.load(tmp_path / "LUT_x2_4bit_int8_s1_{}.npy".format(m)) == out["s1_" + m]).all()

@@ -152,3 +152,22 @@ def test_live_reference_all_fraction_tuples():
         ref = fn(lut.astype(np.float32), x, 1, 1, 4, 4, upscale=up, mode="s")
         out = O.four_simplex_interp(lut, x, 1, 1, 4, 4, up, "s")
         assert (out == ref).all()
+
+
+@needs_ref
+def test_live_reference_transfer_grid(monkeypatch):
+    """mulut_b200.transfer enumerates the LUT grid exactly like the reference's own
+    get_input_tensor / get_mode_input_tensor (sr/2_transfer_to_lut.py:12-66).  The reference calls
+    .cuda() on its index vectors: that single method is neutralised for the call."""
+    import types
+    import torch
+    from mulut_b200 import transfer as T
+    ref = R.transfer_module()
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    for interval in (4, 5):
+        want = ref.get_input_tensor(types.SimpleNamespace(interval=interval))
+        got = T.get_input_tensor(interval)
+        assert got.shape == want.shape and torch.equal(got, want), interval
+    x = T.get_input_tensor(5)
+    for mode in "dy":
+        assert torch.equal(T.get_mode_input_tensor(x, mode), ref.get_mode_input_tensor(x, mode)), mode
