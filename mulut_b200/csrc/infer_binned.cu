@@ -125,6 +125,13 @@ __device__ __forceinline__ void collect_orphans(const uint8_t *__restrict__ img,
     const uint4 *__restrict__ v = reinterpret_cast<const uint4 *>(img);
     const int lane = threadIdx.x & 31;
     constexpr int U = 4;                                     // independent 16-byte loads in flight per thread
+    // byte b of {lut_lo, lut_hi} = 0xFF if bin b is an orphan bin: one PRMT looks up four samples at once
+    uint32_t lut_lo = 0, lut_hi = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        if ((mask >> b) & 1u) lut_lo |= 0xFFu << (8 * b);
+        if ((mask >> (b + 4)) & 1u) lut_hi |= 0xFFu << (8 * b);
+    }
     const size_t stride = (size_t)gridDim.x * blockDim.x * U;
     for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * U; i0 < n16; i0 += stride) {
         uint4 q[U];
@@ -133,32 +140,43 @@ __device__ __forceinline__ void collect_orphans(const uint8_t *__restrict__ img,
             const size_t i = i0 + u * 32 + lane;
             q[u] = i < n16 ? __ldg(v + i) : make_uint4(0, 0, 0, 0);
         }
+        uint32_t hits[U];
+        uint32_t cnt = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
+            const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+            uint32_t h[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t x = (w[k] >> 5) & 0x07070707u;      // the four bins, one per byte
+                x |= x >> 4;                                 // byte 0 = b0 | b1 << 4, byte 2 = b2 | b3 << 4
+                h[k] = __byte_perm(lut_lo, lut_hi, __byte_perm(x, 0u, 0x4420));
+            }
+            hits[u] = 0;
+            if ((h[0] | h[1] | h[2] | h[3]) && (i0 + u * 32 + lane) < n16) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) hits[u] |= (((h[k] & 0x08040201u) * 0x01010101u) >> 24) << (4 * k);
+            }
+            cnt += __popc(hits[u]);
+        }
+        if (!__any_sync(0xffffffffu, cnt != 0)) continue;
+        uint32_t incl = cnt;                                 // one warp scan + one atomic for the U chunks
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t base = 0;
+        if (lane == 31) base = atomicAdd(count, incl);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        uint32_t pos = base + incl - cnt;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            uint32_t hh = hits[u];
             const size_t i = i0 + u * 32 + lane;
-            uint32_t hits = 0;
-            if (i < n16) {
-                const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) hits |= ((mask >> ((w[k] >> (8 * e + 5)) & 7u)) & 1u) << (4 * k + e);
-            }
-            if (!__any_sync(0xffffffffu, hits != 0)) continue;
-            const uint32_t cnt = __popc(hits);
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            uint32_t base = 0;
-            if (lane == 31) base = atomicAdd(count, incl);
-            base = __shfl_sync(0xffffffffu, base, 31);
-            uint32_t pos = base + incl - cnt;
-            while (hits) {
-                const int e = __ffs(hits) - 1;
-                hits &= hits - 1;
+            while (hh) {
+                const int e = __ffs(hh) - 1;
+                hh &= hh - 1;
                 list[pos++] = (uint32_t)(i * 16 + e);
             }
         }
