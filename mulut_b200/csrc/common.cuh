@@ -103,4 +103,16 @@ __device__ __forceinline__ uint32_t rhe_div_clamp_u8(int num, uint32_t den)
     return min(qd, 255u);
 }
 
+// Same with the division replaced by a multiply-high: magic = floor(2^32 / den) + 1 is exact for
+// num * den < 2^32 (here num < 2^16: |S| <= 12 * 16 * 127 plus the 127 * den bias).
+__device__ __forceinline__ uint32_t rhe_magic(uint32_t den) { return 0xFFFFFFFFu / den + 1u; }
+__device__ __forceinline__ uint32_t rhe_div_clamp_u8_magic(int num, uint32_t den, uint32_t magic)
+{
+    const uint32_t n = (uint32_t)max(num, 0);
+    uint32_t qd = __umulhi(n, magic);
+    const uint32_t rm = n - qd * den;
+    qd += (2u * rm > den) || ((2u * rm == den) && (qd & 1u));
+    return min(qd, 255u);
+}
+
 }  // namespace mulut

@@ -204,6 +204,7 @@ combine_kernel(const int16_t *__restrict__ partial, uint8_t *__restrict__ out, s
                int n_modes, int last, BinPlanArgs pa)
 {
     const uint32_t den = last ? 16u * n_modes : 64u * n_modes;
+    const uint32_t magic = rhe_magic(den);
     const int bias = last ? 0 : 127 * (int)den;
     // When the next stage is the binned kernel K1f, this kernel also counts the 8-bin histogram of
     // the bytes it writes (pa.ctl != null) and its last block turns it into K1f's plan.
@@ -226,8 +227,8 @@ combine_kernel(const int16_t *__restrict__ partial, uint8_t *__restrict__ out, s
         uint32_t lo = 0, hi = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            lo |= rhe_div_clamp_u8(s[k] + bias, den) << (8 * k);
-            hi |= rhe_div_clamp_u8(s[4 + k] + bias, den) << (8 * k);
+            lo |= rhe_div_clamp_u8_magic(s[k] + bias, den, magic) << (8 * k);
+            hi |= rhe_div_clamp_u8_magic(s[4 + k] + bias, den, magic) << (8 * k);
         }
         reinterpret_cast<uint2 *>(out)[i] = make_uint2(lo, hi);
         if (pa.ctl) { bc.add_word(lo); bc.add_word(hi); }
@@ -237,7 +238,7 @@ combine_kernel(const int16_t *__restrict__ partial, uint8_t *__restrict__ out, s
              i += (size_t)gridDim.x * blockDim.x) {
             int s = 0;
             for (int m = 0; m < n_modes; ++m) s += partial[(size_t)m * total + i];
-            const uint32_t o = rhe_div_clamp_u8(s + bias, den);
+            const uint32_t o = rhe_div_clamp_u8_magic(s + bias, den, magic);
             out[i] = (uint8_t)o;
             if (pa.ctl) bc.add_byte(o);
         }
@@ -388,6 +389,7 @@ stage_last2_quad_kernel(const __grid_constant__ StageArgs a)
     const int oWC = 2 * WC;                          // output row pitch in bytes
     const uint32_t bias_total = (uint32_t)a.n_modes * 4u * 2048u;   // 16*128 per interpolation
     const uint32_t den = 16u * a.n_modes;
+    const uint32_t magic = rhe_magic(den);
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int tx = (int)(tile % tiles_x);
@@ -437,7 +439,7 @@ stage_last2_quad_kernel(const __grid_constant__ StageArgs a)
 #pragma unroll
                 for (int v = 0; v < 2; ++v) {
                     const int S = (int)tot[u * 2 + v] - (int)bias_total;
-                    so[u * Q2_OP + v * C] = (uint8_t)rhe_div_clamp_u8(S, den);
+                    so[u * Q2_OP + v * C] = (uint8_t)rhe_div_clamp_u8_magic(S, den, magic);
                 }
         }
         __syncthreads();
@@ -533,6 +535,7 @@ stage_last2_cell_kernel(const __grid_constant__ StageArgs a)
     const int oWC = 2 * WC;
     const uint32_t bias_total = (uint32_t)a.n_modes * 4u * 2048u;
     const uint32_t den = 16u * a.n_modes;
+    const uint32_t magic = rhe_magic(den);
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int tx = (int)(tile % tiles_x);
@@ -564,7 +567,7 @@ stage_last2_cell_kernel(const __grid_constant__ StageArgs a)
 #pragma unroll
                 for (int v = 0; v < 2; ++v) {
                     const int S = (int)acc[u * 2 + v] - (int)bias_total;
-                    so[u * Q2_OP + v * C] = (uint8_t)rhe_div_clamp_u8(S, den);
+                    so[u * Q2_OP + v * C] = (uint8_t)rhe_div_clamp_u8_magic(S, den, magic);
                 }
         }
         __syncthreads();
@@ -682,6 +685,7 @@ stage_last4_quad_kernel(const __grid_constant__ StageArgs a)
     const int oWC = 4 * WC;
     const uint32_t bias_total = (uint32_t)a.n_modes * 4u * 2048u;
     const uint32_t den = 16u * a.n_modes;
+    const uint32_t magic = rhe_magic(den);
     // my orbit's four sub-pixel positions (u,v), in rotation order
     int pu[4], pv[4];
 #pragma unroll
@@ -727,7 +731,7 @@ stage_last4_quad_kernel(const __grid_constant__ StageArgs a)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int S = (int)acc[s][i] - (int)bias_total;
-                    so[pu[i] * Q4_OP + pv[i] * C] = (uint8_t)rhe_div_clamp_u8(S, den);
+                    so[pu[i] * Q4_OP + pv[i] * C] = (uint8_t)rhe_div_clamp_u8_magic(S, den, magic);
                 }
             }
         }
