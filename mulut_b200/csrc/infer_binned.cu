@@ -300,10 +300,11 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
     const int n_my = (int)((n_tiles - me + gb - 1) / gb);
 
     auto issue = [&](int i) {                              // thread 0 only: TMA load of my i-th tile
-        const long long tile = me + (long long)i * gb;
-        const int tx = (int)(tile % tiles_x);
-        const long long tr = tile / tiles_x;
-        const int ty = (int)(tr % tiles_y), n = (int)(tr / tiles_y);
+        const unsigned tile = (unsigned)(me + (long long)i * gb);              // n_tiles < 2^31 (checked on the host)
+        const unsigned tr = tile / (unsigned)tiles_x;
+        const int tx = (int)(tile - tr * (unsigned)tiles_x);
+        const int n = (int)(tr / (unsigned)tiles_y);
+        const int ty = (int)(tr - (unsigned)n * (unsigned)tiles_y);
         const int y0 = ty * BN_TH, X0 = tx * BN_TW;
         const int slot = i % BN_RING;
         const int border = (y0 < 2) || (y0 + BN_TH + 2 > a.H) || (X0 < 2 * CT) || (X0 + BN_TW + 2 * CT > WC);
@@ -519,6 +520,7 @@ int launch_stage_binned(const StageArgs &a, void *ctl_mem, uint32_t *list, size_
     if (tma_encode_frames(&tmap, a.in, a.N, a.H, a.W * a.C, BN_BOXW, BN_BOXH) != 0) return 1;   // caller falls back
     BinCtl *ctl = static_cast<BinCtl *>(ctl_mem);
     const BinPlanArgs pa = binned_plan_args(a, ctl_mem, list, list_cap);
+    if (pa.n_tiles >= 0x7fffffffLL) return 1;              // 32-bit tile arithmetic in the kernel
     BinnedArgs b;
     memset(&b, 0, sizeof b);
     b.out = a.out; b.N = a.N; b.H = a.H; b.W = a.W; b.C = a.C; b.n_modes = a.n_modes; b.ctl = ctl;

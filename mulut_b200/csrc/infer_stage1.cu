@@ -91,6 +91,7 @@ stage_smem_tma_kernel(const __grid_constant__ Stage1Args a, const __grid_constan
     const int8_t *slut = reinterpret_cast<const int8_t *>(g1_smem + G1_RING * G1_SLOT);
     __shared__ __align__(8) uint64_t s_full[G1_RING];
     __shared__ __align__(8) uint64_t s_lutbar;
+    __shared__ int4 s_coord[G1_RING];            // frame, y0, X0 of the tile in each ring slot
 
     const int tid = threadIdx.x;
     const int WC = a.W * CT;
@@ -110,18 +111,16 @@ stage_smem_tma_kernel(const __grid_constant__ Stage1Args a, const __grid_constan
     }
     __syncthreads();
 
-    auto tile_coords = [&](int i, int &n, int &y0, int &X0) {
-        const long long tile = me + (long long)i * a.ctas_per_mode;
-        const int tx = (int)(tile % tiles_x);
-        const long long tr = tile / tiles_x;
-        y0 = (int)(tr % tiles_y) * G1_TH;
-        n = (int)(tr / tiles_y);
-        X0 = tx * G1_TW;
-    };
+    // tile -> (frame, y0, X0): computed once per tile by the issuing thread and published with the
+    // tile itself (the mbarrier's release/acquire orders it), not divided out by all 384 threads
     auto issue = [&](int i) {                              // thread 0 only
-        int n, y0, X0;
-        tile_coords(i, n, y0, X0);
+        const unsigned tile = (unsigned)(me + (long long)i * a.ctas_per_mode);      // n_tiles < 2^31 (checked on the host)
+        const unsigned tr = tile / (unsigned)tiles_x;
+        const int X0 = (int)(tile - tr * (unsigned)tiles_x) * G1_TW;
+        const int n = (int)(tr / (unsigned)tiles_y);
+        const int y0 = (int)(tr - (unsigned)n * (unsigned)tiles_y) * G1_TH;
         const int slot = i % G1_RING;
+        s_coord[slot] = make_int4(n, y0, X0, 0);
         const uint32_t bar = smem_u32(&s_full[slot]);
         mbar_expect_tx(bar, G1_SLOT);
         tma_load_3d(smem_u32(s_ring + slot * G1_SLOT), &tmap, X0 - G1_HX, y0 - 2, n, bar);
@@ -139,9 +138,9 @@ stage_smem_tma_kernel(const __grid_constant__ Stage1Args a, const __grid_constan
 
     for (int i = 0; i < n_my; ++i) {
         const int slot = i % G1_RING;
-        int n, y0, X0;
-        tile_coords(i, n, y0, X0);
         mbar_wait(smem_u32(&s_full[slot]), (uint32_t)(i / G1_RING) & 1u);
+        const int4 tc = s_coord[slot];
+        const int n = tc.x, y0 = tc.y, X0 = tc.z;
         uint8_t *tile = s_ring + slot * G1_SLOT;
         const bool border = (y0 < 2) || (y0 + G1_TH + 2 > a.H) || (X0 < 2 * CT) || (X0 + G1_TW + 2 * CT > WC);
         if (border) {
@@ -220,6 +219,7 @@ int launch_stage1_tma(const StageArgs &a, int16_t *partial, cudaStream_t stream)
     for (int m = 0; m < a.n_modes; ++m) { s.modes[m] = a.modes[m]; s.lut_pad[m] = a.lut_alt[m]; }
     const int WC = a.W * a.C;
     const long long n_tiles = (long long)a.N * ((a.H + G1_TH - 1) / G1_TH) * ((WC + G1_TW - 1) / G1_TW);
+    if (n_tiles >= 0x7fffffffLL) return 1;                 // 32-bit tile arithmetic in the kernel
     return a.C == 3 ? launch_stage1_t<3>(s, tmap, a.num_sms, n_tiles, stream)
                     : launch_stage1_t<1>(s, tmap, a.num_sms, n_tiles, stream);
 }
