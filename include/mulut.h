@@ -47,7 +47,7 @@ typedef struct mulut_handle_s *mulut_handle_t;
 #define MULUT_KERNEL_TILED_CELL 2   /* ... up=2 last stage: one lane fetches its cell, 2 x LDG.256 (K1d)  */
 #define MULUT_KERNEL_TILED_BINNED 3 /* ... up=2 last stage: samples binned by value, LUT slabs in shared
                                        memory, TMA tile ring (K1f); needs 16-B aligned frames with
-                                       W*C % 16 == 0 and C in {1,3}, otherwise runs K1c              */
+                                       W*C % 16 == 0 and C <= 4, otherwise runs K1c              */
 
 int mulut_version(void);
 const char *mulut_last_error(void);

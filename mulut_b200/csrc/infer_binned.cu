@@ -474,7 +474,7 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
 bool binned_supported(const StageArgs &a, int up)
 {
     return up == 2 && a.last && a.interval == 4 && a.n_modes >= 1 && a.n_modes <= BN_MAX_MODES &&
-           (a.C == 1 || a.C == 3) && a.lut_slab[0] != nullptr && tma_frame_ok(a.in, a.H, a.W * a.C);
+           a.C >= 1 && a.C <= 4 && a.lut_slab[0] != nullptr && tma_frame_ok(a.in, a.H, a.W * a.C);
 }
 
 template <int CT>
@@ -538,7 +538,10 @@ int launch_stage_binned(const StageArgs &a, void *ctl_mem, uint32_t *list, size_
         *launches += 1;
     }
     prof->begin(MULUT_PROF_LAST_BINNED, stream);
-    int rc = a.C == 3 ? launch_binned_t<3>(b, tmap, a.num_sms, stream) : launch_binned_t<1>(b, tmap, a.num_sms, stream);
+    int rc = a.C == 3 ? launch_binned_t<3>(b, tmap, a.num_sms, stream)
+           : a.C == 1 ? launch_binned_t<1>(b, tmap, a.num_sms, stream)
+           : a.C == 4 ? launch_binned_t<4>(b, tmap, a.num_sms, stream)
+                      : launch_binned_t<2>(b, tmap, a.num_sms, stream);
     prof->end(stream);
     if (rc) return rc;
     *launches += 1;

@@ -186,7 +186,7 @@ stage_smem_tma_kernel(const __grid_constant__ Stage1Args a, const __grid_constan
 
 bool stage1_tma_supported(const StageArgs &a, int up)
 {
-    return up == 1 && a.interval == 4 && a.n_modes >= 1 && (a.C == 1 || a.C == 3) && a.lut_alt[0] != nullptr &&
+    return up == 1 && a.interval == 4 && a.n_modes >= 1 && a.C >= 1 && a.C <= 4 && a.lut_alt[0] != nullptr &&
            tma_frame_ok(a.in, a.H, a.W * a.C);
 }
 
@@ -221,7 +221,9 @@ int launch_stage1_tma(const StageArgs &a, int16_t *partial, cudaStream_t stream)
     const long long n_tiles = (long long)a.N * ((a.H + G1_TH - 1) / G1_TH) * ((WC + G1_TW - 1) / G1_TW);
     if (n_tiles >= 0x7fffffffLL) return 1;                 // 32-bit tile arithmetic in the kernel
     return a.C == 3 ? launch_stage1_t<3>(s, tmap, a.num_sms, n_tiles, stream)
-                    : launch_stage1_t<1>(s, tmap, a.num_sms, n_tiles, stream);
+         : a.C == 1 ? launch_stage1_t<1>(s, tmap, a.num_sms, n_tiles, stream)
+         : a.C == 4 ? launch_stage1_t<4>(s, tmap, a.num_sms, n_tiles, stream)
+                    : launch_stage1_t<2>(s, tmap, a.num_sms, n_tiles, stream);
 }
 
 }  // namespace mulut

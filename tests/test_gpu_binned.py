@@ -24,7 +24,7 @@ def _run(eng, frames):
 
 @pytest.mark.parametrize("C,shape", [(3, (1, 64, 96)), (3, (2, 35, 80)), (3, (3, 97, 208)), (3, (1, 1, 16)),
                                      (3, (1, 2, 16)), (3, (1, 130, 32)), (1, (2, 67, 96)), (1, (1, 33, 208)),
-                                     (1, (1, 5, 16)), (3, (1, 200, 400))])
+                                     (1, (1, 5, 16)), (3, (1, 200, 400)), (2, (2, 40, 48)), (4, (1, 70, 100)), (4, (2, 33, 24))])
 @pytest.mark.parametrize("orphans", ["1", "0"])
 def test_binned_matches_oracle(C, shape, orphans, monkeypatch):
     """orphans=0 keeps every non-empty bin in shared memory (small frames would otherwise be
