@@ -161,7 +161,8 @@ def gather_peak(device):
     out = (ctypes.c_double * 3)()
     res = {}
     for name, table, bps, tpb in [("quad_cell64", 12 << 20, 4, 512), ("ldg_u32", 1 << 20, 4, 512),
-                                  ("lds_u8", 83584, 2, 512), ("lds_u32", 176976, 1, 768)]:
+                                  ("lds_u8", 83584, 2, 512), ("lds_u32", 176976, 1, 768),
+                                  ("quad_cell256_3rows", 50 << 20, 2, 384)]:
         rc = L.mulut_gather_bench(device, _lib.GB_VARIANTS[name], table, 256, bps, tpb, 3, out)
         if rc == 0:
             res[name] = {"gathers_per_s": out[0], "useful_GBps": out[1] / 1e9}
@@ -344,7 +345,9 @@ def main():
         "smem_stage":    (60, 1, 1 + 2 * M, "lds_u8", "K1g/K1a: 1-byte vertex gathers from the shared-memory LUT"),
         "generic_stage": (60, 1, 2, "ldg_u32", "K0: vertex gathers through L1/L2"),
         "last_binned":   (60, r2, 1 + r2, "lds_u32", "K1f: 4-byte vertex-row gathers from shared-memory LUT slabs"),
-        "last_tiled":    (60, r2, 1 + r2, "quad_cell64", "K1c/K1e: 64-byte cell fetches from L1/L2 (one per 5 vertices)"),
+        "last_tiled":    (60, r2, 1 + r2, "quad_cell256_3rows" if SCALE == 4 else "quad_cell64",
+                          "K1e: three 64-byte row-blocks of a 256-byte cell per interpolation (L2)" if SCALE == 4 else
+                          "K1c: 64-byte cell fetches from L1/L2 (one per 5 vertices)"),
         "generic_last":  (60, r2, 1 + r2, "ldg_u32", "K0: vertex gathers through L1/L2"),
         "combine":       (0, 0, 2 * M + 1, None, "K1b: streaming"),
         "bin_hist":      (0, 0, 2, None, "K1f preparation: streaming"),
@@ -378,7 +381,7 @@ def main():
         g = gp.get(variant, {}).get("gathers_per_s")
         if not g:
             return None
-        return g * 5 if variant == "quad_cell64" else g      # one 64-B cell serves the 5 vertices of an interpolation
+        return g * 5 if variant.startswith("quad_cell") else g   # one cell fetch serves the 5 vertices of an interpolation
 
     ach_gathers = samples_per_step * n_gather / per_launch_s if per_launch_s > 0 else 0.0
     pk = peak_gathers(peak_variant) if peak_variant else None

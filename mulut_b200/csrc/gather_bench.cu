@@ -71,7 +71,8 @@ __global__ void gather_kernel(const uint8_t *__restrict__ table, uint32_t n_entr
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else {
-        const bool coop4 = VARIANT == MULUT_GB_QUAD_CELL64;
+        const bool coop4 = VARIANT == MULUT_GB_QUAD_CELL64 || VARIANT == MULUT_GB_QUAD_CELL256_3ROWS ||
+                           VARIANT == MULUT_GB_QUAD_CELL256_4SECT;
         const bool coop2 = VARIANT == MULUT_GB_PAIR_CELL64;
         const bool coop8 = VARIANT == MULUT_GB_OCT_CELL128;
         const uint32_t seed_id = coop4 ? (gtid >> 2) : coop2 ? (gtid >> 1) : coop8 ? (gtid >> 3) : gtid;
@@ -90,6 +91,24 @@ __global__ void gather_kernel(const uint8_t *__restrict__ table, uint32_t n_entr
                 } else if constexpr (VARIANT == MULUT_GB_QUAD_CELL64) {
                     const uint4 v = __ldg(reinterpret_cast<const uint4 *>(table + (size_t)idx * 64 + (lane & 3) * 16));
                     acc += v.x ^ v.y ^ v.z ^ v.w;
+                } else if constexpr (VARIANT == MULUT_GB_QUAD_CELL256_3ROWS) {
+                    // K1e's shape: three of the four 64-B row-blocks of a 256-B cell, 4 lanes x LDG.128 each
+                    const uint8_t *c = table + (size_t)idx * 256 + (lane & 3) * 16;
+                    const uint32_t mid = 64u + 64u * ((idx >> 3) & 1u);
+                    const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(c));
+                    const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(c + mid));
+                    const uint4 v2 = __ldg(reinterpret_cast<const uint4 *>(c + 192));
+                    acc += v0.x ^ v0.y ^ v0.z ^ v0.w ^ v1.x ^ v1.y ^ v1.z ^ v1.w ^ v2.x ^ v2.y ^ v2.z ^ v2.w;
+                } else if constexpr (VARIANT == MULUT_GB_QUAD_CELL256_4SECT) {
+                    // candidate shape: the four 32-B sectors a simplex path touches, one LDG.256 per lane
+                    const uint32_t q = lane & 3;
+                    const uint32_t sect = q == 0 ? 0u : q == 3 ? 7u : q == 1 ? 1u + (idx % 3u) : 4u + ((idx >> 2) % 3u);
+                    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+                    const uint8_t *p = table + (size_t)idx * 256 + sect * 32;
+                    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                                 : "l"(p));
+                    acc += r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7;
                 } else if constexpr (VARIANT == MULUT_GB_OCT_CELL128) {
                     const uint4 v = __ldg(reinterpret_cast<const uint4 *>(table + (size_t)idx * 128 + (lane & 7) * 16));
                     acc += v.x ^ v.y ^ v.z ^ v.w;
@@ -174,6 +193,14 @@ extern "C" int mulut_gather_bench(int device, int variant, size_t table_bytes, i
     case MULUT_GB_OCT_CELL128:
         rc = run_variant<MULUT_GB_OCT_CELL128>(d_table, (uint32_t)(table_bytes / 128), iters, blocks, threads, 0, d_sink, repeats, &ms);
         bytes_per_gather = 128; gathers_per_thread_iter = GB_U / 8.0; break;
+    case MULUT_GB_QUAD_CELL256_3ROWS:
+        rc = run_variant<MULUT_GB_QUAD_CELL256_3ROWS>(d_table, (uint32_t)(table_bytes / 256), iters, blocks, threads, 0, d_sink, repeats, &ms);
+        bytes_per_gather = 192; gathers_per_thread_iter = GB_U / 4.0;
+        break;
+    case MULUT_GB_QUAD_CELL256_4SECT:
+        rc = run_variant<MULUT_GB_QUAD_CELL256_4SECT>(d_table, (uint32_t)(table_bytes / 256), iters, blocks, threads, 0, d_sink, repeats, &ms);
+        bytes_per_gather = 128; gathers_per_thread_iter = GB_U / 4.0;
+        break;
     case MULUT_GB_LDS_U8:
     case MULUT_GB_LDS_U32: {
         if (table_bytes > 200 * 1024) { set_error("shared-memory table must be <= 200 KB"); rc = MULUT_E_BAD_ARG; break; }
