@@ -220,7 +220,7 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="mulut_b200", choices=["mulut_b200", "reference"])
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: per config, 16 for cfg2)")
