@@ -190,6 +190,17 @@ int mulut_adam_step_f32(float *d_param, const float *d_grad, float *d_exp_avg, f
 int mulut_eval_psnr_ssim_y_u8(const uint8_t *d_gt, const uint8_t *d_img, int H, int W, int shave_border,
                               void *d_work, double *out2, void *stream);
 
+/*
+ * The CTA allocation of the binned last-stage kernel (K1f), computed on the HOST with the same code
+ * the device runs: given the 8-bin histogram of the stage input (bin = sample >> 5), the number of
+ * tiles, the CTAs available (one per SM) and the capacity of the orphan list, returns the CTAs dealt
+ * to each bin (0 = bin not resident) and the mask of bins left to the orphan list kernel.
+ * Diagnostic / test entry: no device work.
+ */
+int mulut_plan_bins(const unsigned long long *hist8, long long n_tiles, int n_ctas,
+                    unsigned long long list_cap, int allow_orphans, int *ctas_per_bin8,
+                    unsigned *orphan_mask);
+
 /* Pinned host memory for the *_host entry points. */
 void *mulut_host_alloc(size_t bytes);
 int mulut_host_free(void *p);

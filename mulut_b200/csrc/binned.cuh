@@ -36,7 +36,7 @@ constexpr unsigned long long BN_CV = 1200;      // per tile visit of one CTA (to
 constexpr unsigned long long BN_CS = 11;        // per sample interpolated from shared memory (measured 10.7-14.4)
 constexpr unsigned long long BN_CG = 26;        // per sample interpolated by the list kernel
 
-__device__ inline void bin_plan(BinCtl *__restrict__ ctl, long long n_tiles, int G, unsigned long long list_cap,
+__host__ __device__ inline void bin_plan(BinCtl *__restrict__ ctl, long long n_tiles, int G, unsigned long long list_cap,
                                 int allow_orphans)
 {
     unsigned long long n[BN_BINS], cost[BN_BINS], total = 0, orph = 0;
@@ -61,7 +61,8 @@ __device__ inline void bin_plan(BinCtl *__restrict__ ctl, long long n_tiles, int
     }
     int g[BN_BINS], used = 0;
     for (int b = 0; b < BN_BINS; ++b) {
-        g[b] = cost[b] ? max(1, (int)(cost[b] * (unsigned long long)G / total)) : 0;
+        const int share = (int)(cost[b] * (unsigned long long)G / (total ? total : 1));
+        g[b] = cost[b] ? (share > 1 ? share : 1) : 0;
         used += g[b];
     }
     while (total && used < G) {                             // hand the rest to the most loaded groups

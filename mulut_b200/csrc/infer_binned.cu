@@ -557,6 +557,24 @@ int launch_stage_binned(const StageArgs &a, void *ctl_mem, uint32_t *list, size_
 
 }  // namespace mulut
 
+// Host mirror of the plan the device computes (same code: bin_plan is __host__ __device__) - lets the
+// CPU test-suite check the allocation logic without a GPU.
+extern "C" int mulut_plan_bins(const unsigned long long *hist8, long long n_tiles, int n_ctas, unsigned long long list_cap,
+                               int allow_orphans, int *ctas_per_bin8, unsigned *orphan_mask)
+{
+    if (!hist8 || !ctas_per_bin8 || !orphan_mask || n_tiles < 0 || n_ctas < 1) {
+        mulut::set_error("mulut_plan_bins: bad argument");
+        return MULUT_E_BAD_ARG;
+    }
+    mulut::BinCtl ctl;
+    memset(&ctl, 0, sizeof ctl);
+    for (int b = 0; b < mulut::BN_BINS; ++b) ctl.hist[b] = hist8[b];
+    mulut::bin_plan(&ctl, n_tiles, n_ctas, list_cap, allow_orphans);
+    for (int b = 0; b < mulut::BN_BINS; ++b) ctas_per_bin8[b] = ctl.g[b];
+    *orphan_mask = ctl.orphan_mask;
+    return MULUT_OK;
+}
+
 #ifdef MULUT_BN_TIMING
 // out[8]: mean over CTAs of {wait, fixup, scan, barrier, rounds} cycles, rounds, entries, visits
 extern "C" int mulut_debug_bn_timing(double *out, int n_ctas)

@@ -229,3 +229,51 @@ def test_transfer_grid_enumeration_and_round_trip(tmp_path):
         assert out["s1_" + m].dtype == np.int8 and out["s1_" + m].shape == (L ** 4, 1, 2, 2)
         assert (out["s1_" + m].reshape(-1, 4) == table).all()
         assert (np.load(tmp_path / "LUT_x2_4bit_int8_s1_{}.npy".format(m)) == out["s1_" + m]).all()
+
+
+def _plan(hist, n_tiles, G=148, cap=None, orphans=1):
+    import ctypes
+    from mulut_b200 import _lib
+    h = (ctypes.c_ulonglong * 8)(*[int(x) for x in hist])
+    g = (ctypes.c_int * 8)()
+    mask = ctypes.c_uint()
+    cap = sum(hist) // 4 + 1024 if cap is None else cap
+    assert _lib.lib().mulut_plan_bins(h, n_tiles, G, cap, orphans, g, ctypes.byref(mask)) == 0
+    return list(g), mask.value
+
+
+def test_binned_kernel_plan_properties():
+    """K1f's CTA allocation (host mirror of the device code): every CTA is dealt, empty bins get
+    none, sparse bins become orphans only when allowed and only within the list's capacity, dense
+    bins get CTAs roughly in proportion to their samples."""
+    n_tiles, tile = 32640, 3072
+    total = n_tiles * tile
+    # the benchmark's stage-2 input: two dense bins, two at 0.5 %
+    hist = [0, 0, int(.005 * total), int(.505 * total), int(.485 * total), int(.005 * total), 0, 0]
+    g, mask = _plan(hist, n_tiles)
+    assert sum(g) == 148 and mask == 0b00100100 and g[2] == g[5] == 0 and g[0] == g[7] == 0
+    assert abs(g[3] - g[4]) <= 4 and g[3] + g[4] == 148
+    g, mask = _plan(hist, n_tiles, orphans=0)                   # orphaning off: the sparse bins get CTAs
+    assert mask == 0 and sum(g) == 148 and g[2] >= 1 and g[5] >= 1 and g[3] > 10 * g[2]
+    # uniform: all eight bins resident and equal
+    g, mask = _plan([total // 8] * 8, n_tiles)
+    assert mask == 0 and sum(g) == 148 and max(g) - min(g) <= 1
+    # a single populated bin takes everything; an empty input takes nothing
+    g, mask = _plan([0, 0, 0, 0, 0, 0, total, 0], n_tiles)
+    assert g == [0, 0, 0, 0, 0, 0, 148, 0] and mask == 0
+    g, mask = _plan([0] * 8, n_tiles)
+    assert g == [0] * 8 and mask == 0
+    # tiny frame: everything is cheaper through the list ... unless the list cannot hold it
+    g, mask = _plan([10, 0, 0, 5, 0, 0, 0, 1], 1)
+    assert g == [0] * 8 and mask == 0b10001001
+    g, mask = _plan([10, 0, 0, 5, 0, 0, 0, 1], 1, cap=4)
+    assert mask == 0b10000000 and g[0] >= 1 and g[3] >= 1 and g[7] == 0 and sum(g) == 148
+    # more non-empty bins than CTAs to floor-share: still exactly G in total
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        hist = [int(x) for x in rng.integers(0, 10 ** int(rng.integers(1, 9)), 8)]
+        G = int(rng.integers(8, 200))
+        g, mask = _plan(hist, int(rng.integers(1, 50000)), G=G, orphans=int(rng.integers(0, 2)))
+        resident = [b for b in range(8) if hist[b] and not (mask >> b) & 1]
+        assert all((g[b] > 0) == (b in resident) for b in range(8)), (hist, g, mask)
+        assert sum(g) == (G if resident else 0), (hist, g, mask)
