@@ -514,6 +514,9 @@ __device__ __forceinline__ void stage_bwd_body(const StageF32Args &a, const floa
                 const size_t o_idx = (bc * a.h * UP + (size_t)y * UP + u) * ((size_t)a.w * UP) + (size_t)x * UP + v;
                 g[u * UP + v] = mask[o_idx] ? __fdiv_rn(__ldg(gout + o_idx), a.avg) * inv_q : 0.f;
             }
+        bool any_g = false;
+#pragma unroll
+        for (int j = 0; j < UP2; ++j) any_g |= g[j] != 0.f;
         for (int m = 0; m < a.n_modes; ++m) {
             const int8_t *__restrict__ Q = a.wq[m];
             const uint16_t *__restrict__ FL = a.wflag[m];
@@ -549,7 +552,11 @@ __device__ __forceinline__ void stage_bwd_body(const StageF32Args &a, const floa
                         float c[UP2];
 #pragma unroll
                         for (int j = 0; j < UP2; ++j) c[j] = ((fl >> j) & 1u) ? 127.f * (s.w[k] * gr[j]) : 0.f;
-                        if (!AGG || warp_merge_rows<UP2>(active, s.v[k], c)) {
+                        // a vertex with weight 0 (tied fractions, f = 0: 23 % of the last vertices on noise) or a
+                        // pixel whose output was clamped (g = 0) adds nothing: no atomic for it
+                        bool live = s.w[k] != 0.f && any_g;
+                        if (AGG) live = warp_merge_rows<UP2>(active, live ? s.v[k] : -1 - (int)(threadIdx.x & 31), c) && live;
+                        if (live) {
                             if constexpr (UP2 % 4 == 0) {
 #pragma unroll
                                 for (int j = 0; j < UP2; j += 4) red_add_v4(gw + j, c[j], c[j + 1], c[j + 2], c[j + 3]);
