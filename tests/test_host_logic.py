@@ -277,3 +277,30 @@ def test_binned_kernel_plan_properties():
         resident = [b for b in range(8) if hist[b] and not (mask >> b) & 1]
         assert all((g[b] > 0) == (b in resident) for b in range(8)), (hist, g, mask)
         assert sum(g) == (G if resident else 0), (hist, g, mask)
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Argument checks of the K4 / Adam / metrics entry points return before any CUDA call, so they
+    are testable here: bad mode -> E_BAD_MODE with the reference's message, null buffers -> E_BAD_ARG."""
+    import ctypes
+    from mulut_b200 import _lib
+    L = _lib.lib()
+    assert L.mulut_stage_workspace_bytes(3, 83521, 4) == 3 * (83521 * 16 + ((83521 * 2 + 15) // 16) * 16) + 16
+    assert L.mulut_stage_workspace_bytes(3, 83521, 1) > 0 and L.mulut_stage_workspace_bytes(0, 83521, 4) == 0
+    one = ctypes.c_void_p(16)                  # a non-null, 16-byte aligned dummy: never dereferenced on these paths
+    ptrs = (ctypes.c_void_p * 1)(16)
+    rc = L.mulut_stage_fwd_f32(ptrs, 1, b"e", 83521, 1, 4, one, 1, 1, 4, 4, 4.0, 127.0, one, one, one, None)
+    assert rc == _lib.E_BAD_MODE and "Mode e not implemented." in _lib.last_error()
+    rc = L.mulut_stage_fwd_f32(ptrs, 1, b"s", 100, 1, 4, one, 1, 1, 4, 4, 4.0, 127.0, one, one, one, None)
+    assert rc == _lib.E_LUT_SMALL
+    rc = L.mulut_stage_fwd_f32(ptrs, 1, b"s", 83521, 1, 4, one, 1, 1, 4, 4, 4.0, 127.0, one, one, None, None)
+    assert rc == _lib.E_BAD_ARG and "workspace" in _lib.last_error()
+    rc = L.mulut_stage_bwd_f32(ptrs, 1, b"s", 83521, 5, 4, one, 1, 1, 4, 4, 4.0, 127.0, one, one, one, ptrs, None, None)
+    assert rc == _lib.E_BAD_ARG
+    rc = L.mulut_adam_step_f32(None, one, one, one, 10, one, 0.9, 0.999, 1e-8, 0.0, one, None)
+    assert rc == _lib.E_BAD_ARG
+    out = (ctypes.c_double * 2)()
+    rc = L.mulut_eval_psnr_ssim_y_u8(one, one, 0, 8, 4, one, out, None)
+    assert rc == _lib.E_BAD_ARG
+    with pytest.raises(ValueError):
+        _lib.check(rc)
