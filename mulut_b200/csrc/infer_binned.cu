@@ -10,13 +10,17 @@
 //
 //   * bin b = sample >> 5 (8 bins); a persistent CTA serves ONE bin and keeps
 //     slabs 2b .. 2b+2 of every mode in shared memory (one TMA bulk copy each);
-//   * CTAs are dealt to the bins in proportion to a cost model fed by an 8-bin
-//     histogram of the stage input (bin_hist_kernel), computed identically by
-//     every CTA - no host round trip;
+//   * CTAs are dealt to the bins in proportion to a cost model (bin_plan, binned.cuh)
+//     fed by an 8-bin histogram of the stage input.  The histogram is counted by the
+//     kernel that writes that input (K1b) and its last block runs the plan, or by
+//     bin_hist_kernel for single-stage models - no host round trip; bins too sparse
+//     to pay for walking every tile are left to a list ("orphans") that every CTA
+//     fills for its slice of the input and stage_generic_list_kernel finishes;
 //   * every CTA of a bin walks its share of the halo'd tiles, which arrive through
 //     a ring of TMA tensor-tile loads (cp.async.bulk.tensor.3d + mbarrier, zero
 //     fill outside the frame patched to replicate padding in shared memory);
-//   * a scan compacts the tile's samples of this bin into a queue (ballot/popc);
+//   * a scan compacts the tile's samples of this bin into a queue (one 4-sample word
+//     per thread, zero-byte trick, warp prefix);
 //     full rounds of BN_THREADS queue entries are interpolated, the remainder is
 //     carried to the next tile while its ring slot is still resident;
 //   * per interpolation: keys f<<28 | byte-stride are sorted by a 5-comparator
@@ -84,8 +88,8 @@ int build_slab_major(const int8_t *d_lut, uint8_t *d_slabs, cudaStream_t stream)
 }
 
 // ---------------------------------------------------------------------------
-// control block (device, 256 B, zeroed before every launch) and the three small
-// kernels that prepare a launch: histogram -> plan -> orphan list
+// launch preparation: stand-alone histogram + plan, orphan collection (the control block, the plan
+// and the bin counter live in binned.cuh)
 // ---------------------------------------------------------------------------
 size_t binned_ctl_bytes() { return 256; }
 
