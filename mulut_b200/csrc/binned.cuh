@@ -39,10 +39,14 @@ constexpr unsigned long long BN_CG = 26;        // per sample interpolated by th
 __host__ __device__ inline void bin_plan(BinCtl *__restrict__ ctl, long long n_tiles, int G, unsigned long long list_cap,
                                 int allow_orphans)
 {
+    // (this runs in ONE thread at the tail of the kernel that produced the histogram: keep it short -
+    // independent loads first, float instead of emulated 64-bit division)
     unsigned long long n[BN_BINS], cost[BN_BINS], total = 0, orph = 0;
     bool res[BN_BINS];
+#pragma unroll
+    for (int b = 0; b < BN_BINS; ++b) n[b] = *reinterpret_cast<volatile unsigned long long *>(&ctl->hist[b]);
+#pragma unroll
     for (int b = 0; b < BN_BINS; ++b) {
-        n[b] = *reinterpret_cast<volatile unsigned long long *>(&ctl->hist[b]);
         res[b] = n[b] > 0 && (!allow_orphans || n[b] * (BN_CG - BN_CS) > (unsigned long long)n_tiles * BN_CV);
         if (n[b] && !res[b]) orph += n[b];
     }
@@ -61,7 +65,9 @@ __host__ __device__ inline void bin_plan(BinCtl *__restrict__ ctl, long long n_t
     }
     int g[BN_BINS], used = 0;
     for (int b = 0; b < BN_BINS; ++b) {
-        const int share = (int)(cost[b] * (unsigned long long)G / (total ? total : 1));
+        // floor share in float (24-bit mantissa, G <= a few hundred: at most one CTA off, and the loops
+        // below settle the sum at exactly G either way)
+        const int share = (int)((float)cost[b] * ((float)G / (float)(total ? total : 1)));
         g[b] = cost[b] ? (share > 1 ? share : 1) : 0;
         used += g[b];
     }
