@@ -1,6 +1,6 @@
 """One-off randomised parity sweep of the x2 inference kernels (K1g + K1f / K1c) against the C oracle:
 
-    python tools/fuzz_infer.py <first seed> <last seed>      # on the GPU box
+    python tests/fuzz_infer.py <first seed> <last seed>      # on the GPU box
 
 Random C in 1..4, TMA-mappable widths, 1-3 stages, mode subsets, five value distributions, orphaning on/off.
 Round 1: seeds 0..399, both kernel selections: 0 mismatches."""

@@ -3,10 +3,10 @@
 LUT-gradient all-reduce + Adam), batch 256 of 48x48 patches, x4 sdy 2-stage, shipped
 LUTs.  One process per GPU (torchrun); the batch is split across ranks.
 
-    python tools/finetune_bench.py [--batch 256] [--steps 10] [--aten]
+    python tools/finetune_bench.py [--batch 256] [--steps 50] [--eager] [--smooth]
 
---aten additionally times the plain-ATen restatement of the reference's torch path
-(oracle/interp_torch_oracle.py) on the same GPU: the bar the kernels replace.
+(The plain-ATen restatement of the reference's torch path is timed by tests/aten_restatement_timing.py:
+the oracle is test infrastructure and is not imported from here.)
 Prints one JSON line on rank 0.
 """
 import argparse
@@ -36,7 +36,6 @@ def main():
     ap.add_argument("--crop", type=int, default=48)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=30)
-    ap.add_argument("--aten", action="store_true")
     ap.add_argument("--eager", action="store_true", help="eager launches with per-phase CUDA events instead of the CUDA-graph step")
     ap.add_argument("--smooth", action="store_true", help="low-frequency patches (neighbouring pixels share LUT rows, like natural images) instead of uniform noise")
     ap.add_argument("--loop", action="store_true", help="reference-style loop of 24 InterpTorchBatch calls (K2/K3) instead of the fused stages (K4)")
@@ -125,23 +124,6 @@ def main():
            "breakdown_ms": {k: v / args.steps for k, v in timers.items()} if args.eager else None, "loss": float(loss.item()),
            "allreduce_bytes": bucket.flat.numel() * 4}
 
-    if args.aten and rank == 0:
-        from oracle import interp_torch_oracle as TO
-        ws = {k: torch.tensor(v.astype(np.float32) / 127.0, device=dev, requires_grad=True) for k, v in luts.items()}
-        b = min(per_rank, 32)
-        for _ in range(2):
-            pred = TO.mulut_forward(ws, im[:b], 2, "sdy", 4)
-            F.mse_loss(pred, lb[:b]).backward()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n = 3
-        for _ in range(n):
-            pred = TO.mulut_forward(ws, im[:b], 2, "sdy", 4)
-            F.mse_loss(pred, lb[:b]).backward()
-        torch.cuda.synchronize()
-        res["aten_restatement"] = {"batch": b, "ms_fwd_bwd": (time.perf_counter() - t0) / n * 1e3,
-                                   "note": "sorted-simplex ATen restatement of sr/model.py (oracle), same GPU; the "
-                                           "reference's 24-mask version is slower still"}
     if rank == 0:
         print(json.dumps(res), flush=True)
     if world > 1:
