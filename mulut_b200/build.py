@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 OBJ_DIR = os.path.join(_HERE, "csrc", "build")
 LIB_PATH = os.path.join(_HERE, "libmulut_b200.so")
 SOURCES = ["capi.cu", "tma.cu", "infer_generic.cu", "infer_tiled.cu", "infer_stage1.cu", "infer_binned.cu", "interp_f32.cu", "eval_metrics.cu", "gather_bench.cu"]
-HEADERS = ["common.cuh", "infer.cuh", "tma.cuh", os.path.join("..", "..", "include", "mulut.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "mulut.h")]   # every object depends on every header
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -17,6 +17,7 @@ struct BinCtl {                         // device, 256 B, zeroed before every la
     uint32_t orphan_mask;               // bins left to the L2-gather list kernel
     uint32_t list_count;                // orphan samples collected
     uint32_t ticket;                    // blocks of the histogram producer that have finished
+    uint32_t next_tile[BN_BINS];        // K1f: the next unclaimed tile of each bin (CTAs of a bin claim tiles dynamically)
 };
 static_assert(sizeof(BinCtl) <= 256, "control block");
 
@@ -32,8 +33,8 @@ struct BinPlanArgs {                    // what the plan needs besides the histo
 // A bin is worth a resident CTA group only if its samples outweigh the fixed cost of
 // walking every tile once more (scan + barriers); sparse bins go to a list that the
 // generic L2-gather kernel finishes (stage_generic_list_kernel).  Costs in SM cycles.
-constexpr unsigned long long BN_CV = 1200;      // per tile visit of one CTA (tools/bn_timing.py: 1140-1200)
-constexpr unsigned long long BN_CS = 11;        // per sample interpolated from shared memory (measured 10.7-14.4)
+constexpr unsigned long long BN_CV = 2150;      // per tile visit of one CTA (fit of tools/bn_timing.py's per-bin totals: 2090-2320)
+constexpr unsigned long long BN_CS = 10;        // per sample interpolated from shared memory (same fit: 10.1-10.2)
 constexpr unsigned long long BN_CG = 26;        // per sample interpolated by the list kernel
 
 __host__ __device__ inline void bin_plan(BinCtl *__restrict__ ctl, long long n_tiles, int G, unsigned long long list_cap,

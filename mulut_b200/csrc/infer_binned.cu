@@ -254,7 +254,7 @@ __device__ unsigned long long g_bn_timing[256 * 8];
 #define BN_T0() unsigned long long t_prev = clock64(), t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define BN_T(k) do { if (tid == 0) { const unsigned long long t_now = clock64(); t_acc[k] += t_now - t_prev; t_prev = t_now; } } while (0)
 #define BN_TN(k, n) do { if (tid == 0) t_acc[k] += (n); } while (0)
-#define BN_TEND() do { if (tid == 0) for (int k = 0; k < 8; ++k) g_bn_timing[(blockIdx.x & 255) * 8 + k] = t_acc[k]; } while (0)
+#define BN_TEND() do { if (tid == 0) { t_acc[7] |= (unsigned long long)bin << 48; for (int k = 0; k < 8; ++k) g_bn_timing[(blockIdx.x & 255) * 8 + k] = t_acc[k]; } } while (0)
 #else
 #define BN_T0() do {} while (0)
 #define BN_T(k) do {} while (0)
@@ -296,27 +296,32 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
     }
     __syncthreads();
     const int bin = s_alloc[0], me = s_alloc[1], gb = s_alloc[2];
-    const bool idle = bin >= BN_BINS || me >= n_tiles;
+    const bool idle = bin >= BN_BINS;
     if (idle) {                                            // no tiles for this CTA: it still scans its slice for orphans
         if (a.list && a.ctl->orphan_mask) collect_orphans(a.in, a.total, a.ctl->orphan_mask, &a.ctl->list_count, a.list);
         return;
     }
-    const int n_my = (int)((n_tiles - me + gb - 1) / gb);
+    (void)me; (void)gb;
+    // Tiles are claimed dynamically: the CTAs of a bin draw tile indices from one atomic counter, so a CTA
+    // that lands on tiles rich in its bin (natural frames cluster values in space) simply draws fewer of them.
+    // Thread 0 keeps one claim in flight (`pending`) so the atomic's latency hides behind the rounds.
+    unsigned pending = 0;                                   // thread 0: the tile index claimed for the next issue
 
-    auto issue = [&](int i) {                              // thread 0 only: TMA load of my i-th tile
-        const unsigned tile = (unsigned)(me + (long long)i * gb);              // n_tiles < 2^31 (checked on the host)
+    auto issue = [&](int i, unsigned tile) {               // thread 0 only: TMA load of my i-th tile, or the end marker
+        const int slot = i % BN_RING;
+        if (tile >= (unsigned)n_tiles) { s_info[slot] = make_int4(0, 0, 0, -1); return; }
         const unsigned tr = tile / (unsigned)tiles_x;
         const int tx = (int)(tile - tr * (unsigned)tiles_x);
         const int n = (int)(tr / (unsigned)tiles_y);
         const int ty = (int)(tr - (unsigned)n * (unsigned)tiles_y);
         const int y0 = ty * BN_TH, X0 = tx * BN_TW;
-        const int slot = i % BN_RING;
         const int border = (y0 < 2) || (y0 + BN_TH + 2 > a.H) || (X0 < 2 * CT) || (X0 + BN_TW + 2 * CT > WC);
         s_info[slot] = make_int4(n, y0, X0, border);
         const uint32_t bar = smem_u32(&s_full[slot]);
         mbar_expect_tx(bar, BN_BOXW * BN_BOXH);
         tma_load_3d(smem_u32(s_ring + slot * BN_SLOT), &tmap, X0 - BN_HX, y0 - 2, n, bar);
     };
+    auto claim = [&]() -> unsigned { return atomicAdd(&a.ctl->next_tile[bin], 1u); };     // thread 0 only
 
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
@@ -324,8 +329,14 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
         mbar_expect_tx(lb, (uint32_t)a.n_modes * BN_BIN_BYTES);
         for (int m = 0; m < a.n_modes; ++m)
             bulk_g2s(smem_u32(s_lut + m * BN_BIN_BYTES), a.slabs[m] + (size_t)bin * 2 * BN_SLAB_BYTES, BN_BIN_BYTES, lb);
-        for (int i = 0; i < BN_AHEAD && i < n_my; ++i) issue(i);
+        unsigned t = claim();
+        for (int i = 0; i < BN_AHEAD; ++i) {
+            issue(i, t);
+            if (t < (unsigned)n_tiles) t = claim();        // a CTA draws past the end once, then stops
+        }
+        pending = t;
     }
+    __syncthreads();                                        // s_info of the first tiles is read before any mbarrier wait
     // orphan scan of my slice of the input while the LUT slabs and the first tiles are in flight
     if (a.list && a.ctl->orphan_mask) collect_orphans(a.in, a.total, a.ctl->orphan_mask, &a.ctl->list_count, a.list);
 
@@ -348,11 +359,13 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
     // the two entry counters alternate, and a ring slot is re-filled only after the barrier that
     // follows the rounds that drained it.
     BN_T0();
-    for (int i = 0; i < n_my; ++i) {
+    for (int i = 0;; ++i) {
         const int slot = i % BN_RING;
+        const int4 info = s_info[slot];                    // published by a block barrier at least one tile ago
+        const bool end = info.w < 0;                       // the bin has no more tiles: drain the queue and leave
+        if (!end) {
         mbar_wait(smem_u32(&s_full[slot]), (uint32_t)(i / BN_RING) & 1u);
         BN_T(0);
-        const int4 info = s_info[slot];
         uint8_t *tile = s_ring + slot * BN_SLOT;
         if (info.w) {
             // replicate padding: overwrite the zero-filled out-of-frame cells with the clamped
@@ -406,11 +419,18 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
             const uint32_t c = *reinterpret_cast<volatile uint32_t *>(&s_cnt[i & 1]);
             if (i & 1) { tail += c - seen1; seen1 = c; } else { tail += c - seen0; seen0 = c; }
         }
-        if (tid == 0 && i + BN_AHEAD < n_my) issue(i + BN_AHEAD);
+        if (tid == 0) {                                    // the claim made one tile ago lands here; the next one flies during the rounds
+            const unsigned t = pending;
+            issue(i + BN_AHEAD, t);
+            if (t < (unsigned)n_tiles) pending = claim();
+        }
 #pragma unroll
         for (int k = BN_CARRY; k > 0; --k) bound[k] = bound[k - 1];
         bound[0] = tail;
-        const uint32_t must = (i + 1 == n_my) ? tail : bound[BN_CARRY];
+        } else if (i == 0) {
+            mbar_wait(smem_u32(&s_lutbar), 0u);            // never leave with the slab copy in flight
+        }
+        const uint32_t must = end ? tail : bound[BN_CARRY];
 
         // ---- interpolate: full rounds; a partial round only to release an old ring slot ----
         for (;;) {
@@ -468,6 +488,7 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
         }
         BN_T(4);
         BN_TN(7, 1);
+        if (end) break;
     }
     BN_TEND();
 }
@@ -524,7 +545,7 @@ int launch_stage_binned(const StageArgs &a, void *ctl_mem, uint32_t *list, size_
     if (tma_encode_frames(&tmap, a.in, a.N, a.H, a.W * a.C, BN_BOXW, BN_BOXH) != 0) return 1;   // caller falls back
     BinCtl *ctl = static_cast<BinCtl *>(ctl_mem);
     const BinPlanArgs pa = binned_plan_args(a, ctl_mem, list, list_cap);
-    if (pa.n_tiles >= 0x7fffffffLL) return 1;              // 32-bit tile arithmetic in the kernel
+    if (pa.n_tiles >= 0x7fffffffLL) return 1;              // 32-bit tile arithmetic and tile counters in the kernel
     BinnedArgs b;
     memset(&b, 0, sizeof b);
     b.out = a.out; b.N = a.N; b.H = a.H; b.W = a.W; b.C = a.C; b.n_modes = a.n_modes; b.ctl = ctl;
@@ -580,16 +601,31 @@ extern "C" int mulut_plan_bins(const unsigned long long *hist8, long long n_tile
 }
 
 #ifdef MULUT_BN_TIMING
-// out[8]: mean over CTAs of {wait, fixup, scan, barrier, rounds} cycles, rounds, entries, visits
+// out[8]: mean over CTAs of {wait, fixup, scan, barrier, rounds} cycles, rounds, entries, visits;
+// out[8] = max over CTAs of the five phases' sum, out[9] = mean of it (load balance = out[9] / out[8])
 extern "C" int mulut_debug_bn_timing(double *out, int n_ctas)
 {
     static unsigned long long h[256 * 8];
     if (cudaMemcpyFromSymbol(h, mulut::g_bn_timing, sizeof h) != cudaSuccess) return -1;
     for (int k = 0; k < 8; ++k) {
         double acc = 0;
-        for (int b = 0; b < n_ctas && b < 256; ++b) acc += (double)h[b * 8 + k];
+        for (int b = 0; b < n_ctas && b < 256; ++b) acc += (double)(k == 7 ? h[b * 8 + k] & 0xFFFFFFFFFFFFull : h[b * 8 + k]);
         out[k] = acc / n_ctas;
     }
+    double mx = 0, mean = 0;
+    for (int b = 0; b < n_ctas && b < 256; ++b) {
+        double t = 0;
+        for (int k = 0; k < 5; ++k) t += (double)h[b * 8 + k];
+        mean += t / n_ctas;
+        if (t > mx) mx = t;
+    }
+    out[8] = mx;
+    out[9] = mean;
     return 0;
+}
+// the raw per-CTA counters (256 x 8; the CTA's bin sits in bits 48.. of counter 7)
+extern "C" int mulut_debug_bn_timing_raw(unsigned long long *out)
+{
+    return cudaMemcpyFromSymbol(out, mulut::g_bn_timing, sizeof(unsigned long long) * 256 * 8) == cudaSuccess ? 0 : -1;
 }
 #endif

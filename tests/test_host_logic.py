@@ -254,7 +254,7 @@ def test_binned_kernel_plan_properties():
     assert sum(g) == 148 and mask == 0b00100100 and g[2] == g[5] == 0 and g[0] == g[7] == 0
     assert abs(g[3] - g[4]) <= 4 and g[3] + g[4] == 148
     g, mask = _plan(hist, n_tiles, orphans=0)                   # orphaning off: the sparse bins get CTAs
-    assert mask == 0 and sum(g) == 148 and g[2] >= 1 and g[5] >= 1 and g[3] > 10 * g[2]
+    assert mask == 0 and sum(g) == 148 and g[2] >= 1 and g[5] >= 1 and g[3] > 5 * g[2]
     # uniform: all eight bins resident and equal
     g, mask = _plan([total // 8] * 8, n_tiles)
     assert mask == 0 and sum(g) == 148 and max(g) - min(g) <= 1
