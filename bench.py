@@ -318,6 +318,7 @@ def main():
     value = out_pix_per_step * args.steps / (ms_max * 1e-3) / 1e6
 
     # ---------------- end-to-end leg: host buffers through the C ABI ----------------
+    # (a) one synchronous call per step: the pipeline fills and drains inside every step
     for _ in range(2):
         eng.infer_host(host_in, host_out)
     barrier()
@@ -329,7 +330,26 @@ def main():
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_sync_value = out_pix_per_step * args.steps / float(t.item()) / 1e6
+    # (b) the streaming form (a video pipeline): the same steps enqueued back to back, outputs alternating
+    # between two pinned buffers, one wait at the end - every step's H2D and D2H is still inside the region
+    host_out2 = pinned_empty(host_out.shape)
+    outs = (host_out, host_out2)
+    for i in range(2):
+        eng.infer_host_async(host_in, outs[i & 1])
+    eng.host_sync()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        eng.infer_host_async(host_in, outs[i & 1])
+    eng.host_sync()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = out_pix_per_step * args.steps / float(t.item()) / 1e6
+    if not np.array_equal(host_out2[-1, ::97, ::89], host_out[-1, ::97, ::89]):
+        raise SystemExit("streaming host path: the two output buffers differ")
     sanity = int(host_out[0, :8, :8].sum())    # device->host read of the step's result
 
     # ---------------- the same step on natural-like frames (reported beside the headline) ----------------
@@ -457,7 +477,8 @@ def main():
                        F * H * W * C / 1e6, F * H * W * C * SCALE * SCALE / 1e6),
                    "parallelism": "frames sharded over {} GPU(s), no collective".format(world)},
         "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": F * H * W * C,
-                "d2h_bytes_per_step": F * H * W * C * SCALE * SCALE, "api": "LutEngine.infer_host -> mulut_sr_infer_u8_host",
+                "d2h_bytes_per_step": F * H * W * C * SCALE * SCALE, "api": "LutEngine.infer_host_async x steps + host_sync -> mulut_sr_infer_u8_host_async / mulut_sr_host_sync",
+                "sync_per_step": {"value": e2e_sync_value, "unit": "Mpix/s", "api": "LutEngine.infer_host -> mulut_sr_infer_u8_host, one blocking call per step"},
                 "host_memory": "pinned", "check": sanity},
         "gpu_launches": int(launches) * world,
         "clocks": clocks,

@@ -85,6 +85,15 @@ int mulut_sr_infer_u8(mulut_handle_t handle, const uint8_t *d_in, uint8_t *d_out
 int mulut_sr_infer_u8_host(mulut_handle_t handle, const uint8_t *h_in, uint8_t *h_out,
                            int N, int H, int W, int C);
 
+/* Streaming form of the host path (a video pipeline; the reference keeps its worker pool busy the
+ * same way, sr/4_test_lut.py:257-259): enqueue the batch and return.  Consecutive calls overlap -
+ * the first frames of a call are copied in and computed while the previous call's last frames are
+ * still on their way out.  h_in / h_out must stay valid (and should be pinned) until
+ * mulut_sr_host_sync() returns; results of every enqueued call are complete after it. */
+int mulut_sr_infer_u8_host_async(mulut_handle_t handle, const uint8_t *h_in, uint8_t *h_out,
+                                 int N, int H, int W, int C);
+int mulut_sr_host_sync(mulut_handle_t handle);
+
 /* number of kernel launches issued by this handle since creation */
 long long mulut_launch_count(mulut_handle_t handle);
 

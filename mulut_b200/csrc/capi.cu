@@ -56,6 +56,7 @@ struct mulut_handle_s {
     cudaStream_t lane_stream[HOST_LANES] = {};
     uint8_t *lane_in[HOST_LANES] = {}, *lane_out[HOST_LANES] = {};
     size_t lane_in_bytes = 0, lane_out_bytes = 0;
+    unsigned long long host_k = 0;          // chunks issued on the host path so far (lane = host_k % HOST_LANES)
     long long launches = 0;
     Prof prof;
 };
@@ -387,7 +388,7 @@ int mulut_sr_infer_u8(mulut_handle_t h, const uint8_t *d_in, uint8_t *d_out, int
     return run_stages(h, h->ws[0], d_in, d_out, N, H, W, C, (cudaStream_t)stream);
 }
 
-int mulut_sr_infer_u8_host(mulut_handle_t h, const uint8_t *h_in, uint8_t *h_out, int N, int H, int W, int C)
+int mulut_sr_infer_u8_host_async(mulut_handle_t h, const uint8_t *h_in, uint8_t *h_out, int N, int H, int W, int C)
 {
     int rc = check_shape(h, h_in, h_out, N, H, W, C);
     if (rc) return rc;
@@ -420,9 +421,10 @@ int mulut_sr_infer_u8_host(mulut_handle_t h, const uint8_t *h_in, uint8_t *h_out
         }
         h->lane_in_bytes = cin; h->lane_out_bytes = cout;
     }
-    int k = 0;
-    for (int n = 0; n < N; n += chunk, ++k) {
-        const int lane = k % HOST_LANES;
+    // the lane counter lives in the handle: consecutive calls keep the round robin going, so the
+    // first frames of call j+1 overlap the last D2H of call j (streams order the reuse of a lane)
+    for (int n = 0; n < N; n += chunk, ++h->host_k) {
+        const int lane = (int)(h->host_k % HOST_LANES);
         const int cn = N - n < chunk ? N - n : chunk;
         cudaStream_t st = h->lane_stream[lane];
         MULUT_CUDA(cudaMemcpyAsync(h->lane_in[lane], h_in + (size_t)n * fin, fin * cn, cudaMemcpyHostToDevice, st));
@@ -430,8 +432,22 @@ int mulut_sr_infer_u8_host(mulut_handle_t h, const uint8_t *h_in, uint8_t *h_out
         if (rc) return rc;
         MULUT_CUDA(cudaMemcpyAsync(h_out + (size_t)n * fout, h->lane_out[lane], fout * cn, cudaMemcpyDeviceToHost, st));
     }
+    return MULUT_OK;
+}
+
+int mulut_sr_host_sync(mulut_handle_t h)
+{
+    if (!h) { set_error("mulut_sr_host_sync: null handle"); return MULUT_E_BAD_ARG; }
+    MULUT_CUDA(cudaSetDevice(h->device));
     for (int i = 0; i < HOST_LANES; ++i) MULUT_CUDA(cudaStreamSynchronize(h->lane_stream[i]));
     return MULUT_OK;
+}
+
+int mulut_sr_infer_u8_host(mulut_handle_t h, const uint8_t *h_in, uint8_t *h_out, int N, int H, int W, int C)
+{
+    const int rc = mulut_sr_infer_u8_host_async(h, h_in, h_out, N, H, W, C);
+    if (rc) { if (h) mulut_sr_host_sync(h); return rc; }
+    return mulut_sr_host_sync(h);
 }
 
 void *mulut_host_alloc(size_t bytes)

@@ -64,6 +64,7 @@ class LutEngine:
         self.modes = _check_modes(modes)
         self.stages, self.scale, self.interval, self.device = int(stages), int(scale), int(interval), int(device)
         self._h = ctypes.c_void_p()
+        self._pending = []
         tabs = []
         rows = None
         for s in range(self.stages):
@@ -172,6 +173,27 @@ class LutEngine:
             raise ValueError("bad out array")
         _lib.check(_lib.lib().mulut_sr_infer_u8_host(self._h, a.ctypes.data, o.ctypes.data, N, H, W, C))
         return o[0] if squeeze else o
+
+    def infer_host_async(self, frames: np.ndarray, out: np.ndarray) -> None:
+        """Streaming form of :meth:`infer_host`: enqueue (N,H,W,C) uint8 `frames` -> `out` and return.
+        Consecutive calls overlap (the copy-in and kernels of a call run under the copy-out of the one
+        before).  Both arrays must be C-contiguous uint8, should be pinned (:func:`pinned_empty`) and must
+        not be touched until :meth:`host_sync` returns."""
+        if not (isinstance(frames, np.ndarray) and isinstance(out, np.ndarray) and frames.dtype == np.uint8 and
+                out.dtype == np.uint8 and frames.flags.c_contiguous and out.flags.c_contiguous and frames.ndim == 4):
+            raise ValueError("infer_host_async expects C-contiguous uint8 (N,H,W,C) arrays")
+        N, H, W, C = frames.shape
+        if out.shape != (N, H * self.scale, W * self.scale, C):
+            raise ValueError("bad out array")
+        self._pending.append((frames, out))                      # keep the buffers alive until host_sync
+        _lib.check(_lib.lib().mulut_sr_infer_u8_host_async(self._h, frames.ctypes.data, out.ctypes.data, N, H, W, C))
+
+    def host_sync(self) -> None:
+        """Wait for every :meth:`infer_host_async` call issued so far."""
+        try:
+            _lib.check(_lib.lib().mulut_sr_host_sync(self._h))
+        finally:
+            self._pending.clear()
 
     def __call__(self, frames, out=None):
         """numpy in -> numpy out (host path); CUDA tensor in -> CUDA tensor out."""
