@@ -62,6 +62,8 @@ bool tiled_supported(int up, int interval, int n_modes);
 // K1g, the TMA-fed shared-memory kernel for up = 1 stages (infer_stage1.cu); same int16 partial
 // planes as K1a.  Returns MULUT_OK, an error (< 0) or +1 (frames not TMA-mappable: run K1a).
 bool stage1_tma_supported(const StageArgs &a, int up);
+size_t stage1_pair_bytes();
+int build_pair_table(const int8_t *d_lut_vertex_major, uint8_t *d_pair, cudaStream_t stream);
 int launch_stage1_tma(const StageArgs &a, int16_t *partial, cudaStream_t stream);
 
 // K1f, the binned shared-memory kernel for the up = 2 last stage (infer_binned.cu).

@@ -762,7 +762,7 @@ __global__ void build_cell_major2_kernel(const int8_t *__restrict__ lut, uint8_t
 
 size_t cell_major_bytes(int up)
 {
-    if (up == 1) return LUT1_SMEM;
+    if (up == 1) return LUT1_SMEM + stage1_pair_bytes();     // [padded int8 table | a-paired 16-bit table of K1h]
     if (up == 2) return (size_t)65536 * 64;
     if (up == 4) return (size_t)65536 * 256;
     return 0;
@@ -773,7 +773,7 @@ int build_cell_major(const int8_t *d_lut, uint8_t *d_alt, int up, cudaStream_t s
     if (up == 1) {
         MULUT_CUDA(cudaMemsetAsync(d_alt, 0, LUT1_SMEM, stream));
         MULUT_CUDA(cudaMemcpyAsync(d_alt, d_lut, LUT1_ROWS, cudaMemcpyDeviceToDevice, stream));
-        return MULUT_OK;
+        return build_pair_table(d_lut, d_alt + LUT1_SMEM, stream);
     }
     if (up == 2) {
         build_cell_major2_kernel<<<1024, 256, 0, stream>>>(d_lut, d_alt);
