@@ -215,13 +215,21 @@ combine_kernel(const int16_t *__restrict__ partial, uint8_t *__restrict__ out, s
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
          i += (size_t)gridDim.x * blockDim.x) {
         int s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int m = 0; m < n_modes; ++m) {
-            const int4 v = __ldg(reinterpret_cast<const int4 *>(partial + (size_t)m * total) + i);
-            const int w[4] = {v.x, v.y, v.z, v.w};
+        // the planes' loads are issued together (groups of four modes): bytes in flight, not instructions, bound this kernel
+        for (int m0 = 0; m0 < n_modes; m0 += 4) {
+            int4 v[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                s[2 * k] += (int)(int16_t)(w[k] & 0xffff);
-                s[2 * k + 1] += w[k] >> 16;
+            for (int j = 0; j < 4; ++j)
+                v[j] = (m0 + j < n_modes) ? __ldg(reinterpret_cast<const int4 *>(partial + (size_t)(m0 + j) * total) + i)
+                                          : make_int4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    s[2 * k] += (int)(int16_t)(w[k] & 0xffff);
+                    s[2 * k + 1] += w[k] >> 16;
+                }
             }
         }
         uint32_t lo = 0, hi = 0;
