@@ -8,7 +8,7 @@
 namespace mulut {
 
 constexpr int BN_TW = 96;                       // tile width, byte columns (multiple of C for C <= 4)
-constexpr int BN_TH = 32;                       // tile rows
+constexpr int BN_TH = 16;                       // tile rows
 constexpr int BN_BINS = 8;
 
 struct BinCtl {                         // device, 256 B, zeroed before every launch
@@ -33,7 +33,7 @@ struct BinPlanArgs {                    // what the plan needs besides the histo
 // A bin is worth a resident CTA group only if its samples outweigh the fixed cost of
 // walking every tile once more (scan + barriers); sparse bins go to a list that the
 // generic L2-gather kernel finishes (stage_generic_list_kernel).  Costs in SM cycles.
-constexpr unsigned long long BN_CV = 2150;      // per tile visit of one CTA (fit of tools/bn_timing.py's per-bin totals: 2090-2320)
+constexpr unsigned long long BN_CV = 1050;      // per visit of a 96 x 16 tile (fit of tools/bn_timing.py's per-bin totals: 975-1085)
 constexpr unsigned long long BN_CS = 10;        // per sample interpolated from shared memory (same fit: 10.1-10.2)
 constexpr unsigned long long BN_CG = 26;        // per sample interpolated by the list kernel
 

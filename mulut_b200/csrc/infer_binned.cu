@@ -16,12 +16,15 @@
 //     bin_hist_kernel for single-stage models - no host round trip; bins too sparse
 //     to pay for walking every tile are left to a list ("orphans") that every CTA
 //     fills for its slice of the input and stage_generic_list_kernel finishes;
-//   * every CTA of a bin walks its share of the halo'd tiles, which arrive through
+//   * the CTA runs as BN_GROUPS independent groups of BN_GT threads (own tile ring, queue and named
+//     barrier, shared LUT slabs), so one group's scan / barrier / TMA wait hides behind the other's
+//     interpolation rounds; every group draws tiles of its bin from the bin's atomic counter;
+//   * the halo'd tiles arrive through
 //     a ring of TMA tensor-tile loads (cp.async.bulk.tensor.3d + mbarrier, zero
 //     fill outside the frame patched to replicate padding in shared memory);
 //   * a scan compacts the tile's samples of this bin into a queue (one 4-sample word
 //     per thread, zero-byte trick, warp prefix);
-//     full rounds of BN_THREADS queue entries are interpolated, the remainder is
+//     full rounds of BN_GT queue entries are interpolated, the remainder is
 //     carried to the next tile while its ring slot is still resident;
 //   * per interpolation: keys f<<28 | byte-stride are sorted by a 5-comparator
 //     min/max network, the vertex chain is v0, v0+s1, v0+s1+s2, v4-s4, v4 with
@@ -50,21 +53,24 @@ constexpr int BN_HX = 16;                       // box column of the tile's firs
 constexpr int BN_BOXW = 128;                    // HX + TW + 2*C rounded up to 16 B (C <= 4)
 constexpr int BN_BOXH = BN_TH + 4;
 constexpr int BN_SLOT = BN_BOXW * BN_BOXH;      // 4608 B per ring slot, 128-B aligned
-constexpr int BN_RING = 8;
-constexpr int BN_AHEAD = 3;                     // TMA prefetch distance in tiles
+constexpr int BN_RING = 6;
+constexpr int BN_AHEAD = 2;                     // TMA prefetch distance in tiles
 constexpr int BN_CARRY = BN_RING - BN_AHEAD - 1;   // tiles a queue entry may outlive its scan
-constexpr int BN_THREADS = 768;                 // 24 warps (1024 threads fit at 62 registers but measured no faster)
-constexpr int BN_SCAN_THREADS = 768;            // TW/4 x TH words of a tile, one per scanning thread
-constexpr int BN_QCAP = 8192;                   // queue capacity: power of two > (THREADS - 1 + TW*TH) + TW*TH
+constexpr int BN_GROUPS = 2;                    // independent tile pipelines per CTA (own ring, queue, named barrier): one
+                                                // group's scan / barrier / TMA wait hides behind the other's rounds
+constexpr int BN_GT = 384;                      // threads per group
+constexpr int BN_THREADS = BN_GROUPS * BN_GT;   // 24 warps (1024 threads fit at 62 registers but measured no faster)
+constexpr int BN_SCAN_THREADS = BN_GT;          // TW/4 x TH words of a tile, one per scanning thread
+constexpr int BN_QCAP = 4096;                   // queue capacity per group: power of two > (GT - 1 + TW*TH) + TW*TH
 constexpr int BN_SLAB_WORDS = 4916;             // 17^3 = 4913 rows, padded so a slab is a 16-B multiple
 constexpr int BN_SLAB_BYTES = BN_SLAB_WORDS * 4;
 constexpr int BN_BIN_BYTES = 3 * BN_SLAB_BYTES; // slabs 2b, 2b+1, 2b+2 of one mode
 constexpr int BN_MAX_MODES = 3;
-constexpr size_t BN_SMEM = (size_t)BN_RING * BN_SLOT + BN_QCAP * 2 + (size_t)BN_MAX_MODES * BN_BIN_BYTES;
+constexpr size_t BN_SMEM = (size_t)BN_GROUPS * (BN_RING * BN_SLOT + BN_QCAP * 2) + (size_t)BN_MAX_MODES * BN_BIN_BYTES;
 
-static_assert(BN_TW / 4 * BN_TH == BN_SCAN_THREADS && BN_SCAN_THREADS % 32 == 0 && BN_SCAN_THREADS <= BN_THREADS,
+static_assert(BN_TW / 4 * BN_TH == BN_SCAN_THREADS && BN_SCAN_THREADS % 32 == 0 && BN_SCAN_THREADS <= BN_GT,
               "scan mapping: one 4-sample word per scanning thread, whole warps");
-static_assert(BN_QCAP >= BN_THREADS + 2 * BN_TW * BN_TH, "queue too small");
+static_assert(BN_QCAP >= BN_GT + 2 * BN_TW * BN_TH, "queue too small");
 static_assert(BN_HX + BN_TW + 2 * 4 <= BN_BOXW && 2 * 4 <= BN_HX, "box too narrow for C <= 4");
 
 size_t slab_major_bytes() { return (size_t)17 * BN_SLAB_BYTES; }
@@ -252,9 +258,9 @@ struct BinnedArgs {
 #ifdef MULUT_BN_TIMING
 __device__ unsigned long long g_bn_timing[256 * 8];
 #define BN_T0() unsigned long long t_prev = clock64(), t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
-#define BN_T(k) do { if (tid == 0) { const unsigned long long t_now = clock64(); t_acc[k] += t_now - t_prev; t_prev = t_now; } } while (0)
-#define BN_TN(k, n) do { if (tid == 0) t_acc[k] += (n); } while (0)
-#define BN_TEND() do { if (tid == 0) { t_acc[7] |= (unsigned long long)bin << 48; for (int k = 0; k < 8; ++k) g_bn_timing[(blockIdx.x & 255) * 8 + k] = t_acc[k]; } } while (0)
+#define BN_T(k) do { if (threadIdx.x == 0) { const unsigned long long t_now = clock64(); t_acc[k] += t_now - t_prev; t_prev = t_now; } } while (0)
+#define BN_TN(k, n) do { if (threadIdx.x == 0) t_acc[k] += (n); } while (0)
+#define BN_TEND() do { if (threadIdx.x == 0) { t_acc[7] |= (unsigned long long)bin << 48; for (int k = 0; k < 8; ++k) g_bn_timing[(blockIdx.x & 255) * 8 + k] = t_acc[k]; } } while (0)
 #else
 #define BN_T0() do {} while (0)
 #define BN_T(k) do {} while (0)
@@ -267,32 +273,37 @@ __global__ void __launch_bounds__(BN_THREADS, 1)
 stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(128) uint8_t bn_smem[];
-    uint8_t *s_ring = bn_smem;
-    uint16_t *s_queue = reinterpret_cast<uint16_t *>(bn_smem + BN_RING * BN_SLOT);
-    uint8_t *s_lut = bn_smem + BN_RING * BN_SLOT + BN_QCAP * 2;
-    __shared__ __align__(8) uint64_t s_full[BN_RING];
+    const int grp = threadIdx.x / BN_GT, tid = threadIdx.x - grp * BN_GT, lane = tid & 31;   // tid: index within the group
+    uint8_t *s_ring = bn_smem + grp * (BN_RING * BN_SLOT);
+    uint16_t *s_queue = reinterpret_cast<uint16_t *>(bn_smem + BN_GROUPS * BN_RING * BN_SLOT + grp * (BN_QCAP * 2));
+    uint8_t *s_lut = bn_smem + BN_GROUPS * (BN_RING * BN_SLOT + BN_QCAP * 2);
+    __shared__ __align__(8) uint64_t s_full_all[BN_GROUPS][BN_RING];
     __shared__ __align__(8) uint64_t s_lutbar;
-    __shared__ int4 s_info[BN_RING];             // n, y0, X0, border
-    __shared__ uint32_t s_cnt[2];                // entries queued by even / odd tiles (monotonic)
+    __shared__ int4 s_info_all[BN_GROUPS][BN_RING];   // n, y0, X0, border
+    __shared__ uint32_t s_cnt_all[BN_GROUPS][2];      // entries queued by even / odd tiles (monotonic)
     __shared__ int s_alloc[3];                   // bin, index within bin, CTAs of the bin
+    uint64_t *s_full = s_full_all[grp];
+    int4 *s_info = s_info_all[grp];
+    uint32_t *s_cnt = s_cnt_all[grp];
 
-    const int tid = threadIdx.x, lane = tid & 31;
     const int WC = a.W * CT;
     const int tiles_x = (WC + BN_TW - 1) / BN_TW;
     const int tiles_y = (a.H + BN_TH - 1) / BN_TH;
     const long long n_tiles = (long long)a.N * tiles_y * tiles_x;
 
     // ---- my bin: the plan kernel dealt g[b] CTAs to bin b (same answer in every CTA) ----
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         int g[BN_BINS];
         for (int b = 0; b < BN_BINS; ++b) g[b] = a.ctl->g[b];
         int idx = blockIdx.x, b = 0;
         while (b < BN_BINS && idx >= g[b]) { idx -= g[b]; ++b; }
         s_alloc[0] = b; s_alloc[1] = idx; s_alloc[2] = b < BN_BINS ? g[b] : 1;
-        for (int i = 0; i < BN_RING; ++i) mbar_init(smem_u32(&s_full[i]), 1);
+        for (int g2 = 0; g2 < BN_GROUPS; ++g2) {
+            for (int i = 0; i < BN_RING; ++i) mbar_init(smem_u32(&s_full_all[g2][i]), 1);
+            s_cnt_all[g2][0] = 0; s_cnt_all[g2][1] = 0;
+        }
         mbar_init(smem_u32(&s_lutbar), 1);
         mbar_fence_init();
-        s_cnt[0] = 0; s_cnt[1] = 0;
     }
     __syncthreads();
     const int bin = s_alloc[0], me = s_alloc[1], gb = s_alloc[2];
@@ -323,12 +334,14 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
     };
     auto claim = [&]() -> unsigned { return atomicAdd(&a.ctl->next_tile[bin], 1u); };     // thread 0 only
 
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap);
         const uint32_t lb = smem_u32(&s_lutbar);
         mbar_expect_tx(lb, (uint32_t)a.n_modes * BN_BIN_BYTES);
         for (int m = 0; m < a.n_modes; ++m)
             bulk_g2s(smem_u32(s_lut + m * BN_BIN_BYTES), a.slabs[m] + (size_t)bin * 2 * BN_SLAB_BYTES, BN_BIN_BYTES, lb);
+    }
+    if (tid == 0) {                                         // each group's leader starts its own pipeline
         unsigned t = claim();
         for (int i = 0; i < BN_AHEAD; ++i) {
             issue(i, t);
@@ -370,7 +383,7 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
         if (info.w) {
             // replicate padding: overwrite the zero-filled out-of-frame cells with the clamped
             // in-frame value (always inside this tile, never written by this pass, never read by the scan)
-            for (int idx = tid; idx < BN_BOXW * BN_BOXH; idx += BN_THREADS) {
+            for (int idx = tid; idx < BN_BOXW * BN_BOXH; idx += BN_GT) {
                 const int r = idx / BN_BOXW, j = idx - r * BN_BOXW;
                 const int gy = info.y - 2 + r, gx = info.z - BN_HX + j;
                 const int cy = clampi(gy, 0, a.H - 1);
@@ -413,7 +426,7 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
         }
         BN_T(2);
         if (i == 0) mbar_wait(smem_u32(&s_lutbar), 0u);
-        __syncthreads();
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(BN_GT) : "memory");     // the group's barrier
         BN_T(3);
         {
             const uint32_t c = *reinterpret_cast<volatile uint32_t *>(&s_cnt[i & 1]);
@@ -436,7 +449,7 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
         for (;;) {
             const uint32_t avail = tail - head;
             uint32_t n;
-            if (avail >= BN_THREADS) n = BN_THREADS;
+            if (avail >= BN_GT) n = BN_GT;
             else if ((int)(must - head) > 0) n = avail;
             else break;
             if ((uint32_t)tid < n) {
