@@ -304,3 +304,43 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     assert rc == _lib.E_BAD_ARG
     with pytest.raises(ValueError):
         _lib.check(rc)
+
+
+def test_paired_threshold_form_equals_sorted_simplex_weights():
+    """K1h (csrc/infer_stage1.cu) interpolates with a 3-key sort and a-paired table entries: vertex
+    (u_j, a not stepped) weighs (g_j - g_{j+1}) - (c_j - c_{j+1}) and (u_j, a stepped) c_j - c_{j+1},
+    c_j = min(g_j, f_a).  Exhaustively over all 16^4 fraction tuples this puts the same weight on every
+    corner of the 4-D cell as the reference's sorted-fraction form (sr/4_test_lut.py:53-237; ties are
+    zero-width intervals, so the tie order cannot matter)."""
+    f = np.stack(np.meshgrid(*[np.arange(16)] * 4, indexing="ij"), -1).reshape(-1, 4)       # (65536, 4): fa fb fc fd
+    n = f.shape[0]
+    rows = np.arange(n)
+    # reference form: sort the four fractions descending (stable), walk the vertex chain
+    order = np.argsort(-f, axis=1, kind="stable")
+    fs = np.take_along_axis(f, order, 1)
+    w_ref = np.zeros((n, 16), dtype=np.int64)                 # weight per corner, corner = bitmask of stepped axes
+    corner = np.zeros(n, dtype=np.int64)
+    w = np.concatenate([16 - fs[:, :1], fs[:, :-1] - fs[:, 1:], fs[:, 3:]], 1)
+    for k in range(5):
+        np.add.at(w_ref, (rows, corner), w[:, k])
+        if k < 4:
+            corner = corner | (1 << order[:, k])
+    # K1h form: sort b, c, d only; a enters through c_j = min(g_j, fa)
+    fa = f[:, 0]
+    o3 = np.argsort(-f[:, 1:], axis=1, kind="stable")
+    g = np.take_along_axis(f[:, 1:], o3, 1)
+    gj = np.concatenate([np.full((n, 1), 16), g, np.zeros((n, 1), dtype=g.dtype)], 1)      # g0..g4
+    cj = np.minimum(gj, fa[:, None])
+    q = gj + 255 * cj                                           # the kernel's packed Q_j = g_j + 255 c_j
+    wp = q[:, :-1] - q[:, 1:]                                   # alpha | beta << 8
+    alpha, beta = wp & 255, wp >> 8
+    assert (alpha >= 0).all() and (alpha <= 16).all() and (beta >= 0).all() and (beta <= 16).all()
+    w_new = np.zeros((n, 16), dtype=np.int64)
+    corner = np.zeros(n, dtype=np.int64)
+    for j in range(4):
+        np.add.at(w_new, (rows, corner), alpha[:, j])
+        np.add.at(w_new, (rows, corner | 1), beta[:, j])        # bit 0 = axis a stepped
+        if j < 3:
+            corner = corner | (1 << (o3[:, j] + 1))
+    assert (w_ref.sum(1) == 16).all()
+    assert (w_new == w_ref).all()
