@@ -36,6 +36,8 @@ struct Workspace {
     void *bn_ctl = nullptr;                 // control block of the binned kernel (histogram, plan)
     uint32_t *bn_list = nullptr;            // its orphan-sample list
     size_t bn_list_cap = 0;
+    uint8_t *pitched = nullptr;             // staging copy of a stage input whose rows TMA cannot map in place
+    size_t pitched_bytes = 0;
 };
 
 }  // namespace mulut
@@ -93,6 +95,7 @@ static int ws_reserve(Workspace &w, int stages, int n_modes, size_t frame_sample
 static void ws_free(Workspace &w)
 {
     cudaFree(w.img[0]); cudaFree(w.img[1]); cudaFree(w.partial); cudaFree(w.bn_ctl); cudaFree(w.bn_list);
+    cudaFree(w.pitched);
     w = Workspace();
 }
 
@@ -100,6 +103,45 @@ static bool uses_tiled(const mulut_handle_s *h, int up, int C)
 {
     if (h->kernel == MULUT_KERNEL_GENERIC) return false;
     return tiled_supported(up, h->interval, h->n_modes) && (C >= 1 && C <= 4);
+}
+
+// dense rows -> rows `pitch` bytes apart (the padding is never read: TMA's tensor is WC wide)
+__global__ void repack_pitch_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t rows, int WC, int pitch)
+{
+    const int wpr = pitch / 4;                                     // words per output row
+    const size_t words = rows * (size_t)wpr;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / wpr;
+        const int c = (int)(i - r * wpr) * 4;
+        const uint8_t *src = in + r * (size_t)WC + c;
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c + k < WC) v |= (uint32_t)src[k] << (8 * k);
+        reinterpret_cast<uint32_t *>(out)[i] = v;
+    }
+}
+
+// Where TMA can read the frames at `img`: in place when they are 16-byte aligned with a row length that is
+// a multiple of 16, otherwise a pitched copy in the workspace (one extra read + write of the input, < 1 % of a stage).
+static int tma_view(Workspace &w, StageArgs &a, int num_sms, cudaStream_t stream, int *launches)
+{
+    const int WC = a.W * a.C;
+    if (tma_mappable(a.in, a.H, WC)) { a.in_tma = a.in; a.in_pitch = WC; return MULUT_OK; }
+    const int pitch = (WC + 15) / 16 * 16;
+    const size_t rows = (size_t)a.N * a.H, need = rows * (size_t)pitch;
+    if (w.pitched_bytes < need) {
+        cudaFree(w.pitched); w.pitched = nullptr; w.pitched_bytes = 0;
+        MULUT_CUDA(cudaMalloc(&w.pitched, need));
+        w.pitched_bytes = need;
+    }
+    size_t blocks = (need / 4 + 255) / 256;
+    if (blocks > (size_t)num_sms * 16) blocks = (size_t)num_sms * 16;
+    repack_pitch_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.in, w.pitched, rows, WC, pitch);
+    MULUT_CUDA(cudaGetLastError());
+    a.in_tma = w.pitched; a.in_pitch = pitch;
+    *launches += 1;
+    return MULUT_OK;
 }
 
 static int run_stages(mulut_handle_s *h, Workspace &w, const uint8_t *d_in, uint8_t *d_out, int N, int H, int W,
@@ -142,7 +184,15 @@ static int run_stages(mulut_handle_s *h, Workspace &w, const uint8_t *d_in, uint
         // amortise one 177 KB LUT load per SM; it falls through to K1c when TMA cannot map the frames.
         const bool bin_policy = h->kernel == MULUT_KERNEL_TILED_BINNED ||
                                 (h->kernel == MULUT_KERNEL_AUTO && samples >= (1u << 20));
-        if (uses_tiled(h, up, C) && binned_supported(a, up) && bin_policy) {
+        // the TMA-fed kernels (K1h for up = 1, K1f for the x2 last stage) read the input through a tensor map
+        const bool k1f = uses_tiled(h, up, C) && binned_supported(a, up) && bin_policy;
+        if (uses_tiled(h, up, C) && !a.no_tma && h->interval == 4 && (k1f || up == 1)) {
+            int launches = 0;
+            rc = tma_view(w, a, h->num_sms, stream, &launches);
+            if (rc) return rc;
+            h->launches += launches;
+        }
+        if (k1f && a.in_tma) {
             int launches = 0;
             done = launch_stage_binned(a, w.bn_ctl, w.bn_list, w.bn_list_cap, planned, stream, &launches, &h->prof);
             if (done < 0) return done;

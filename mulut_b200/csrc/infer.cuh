@@ -13,6 +13,8 @@ struct StageArgs {
     int interval;
     int last;                                // last stage: up = scale, avg = M, bias 0
     int no_tma;                              // force the pre-TMA kernels (K1a) for cross-checks
+    const uint8_t *in_tma;                   // the same frames where TMA can map them (16-B aligned, rows in_pitch apart), or null
+    int in_pitch;
     int num_sms;
     const int8_t *lut[MULUT_MAX_MODES];      // reference layout: int8 (L^4, up^2)
     const uint8_t *lut_alt[MULUT_MAX_MODES]; // device re-layout used by the tiled kernels
@@ -61,6 +63,7 @@ bool tiled_supported(int up, int interval, int n_modes);
 
 // K1g, the TMA-fed shared-memory kernel for up = 1 stages (infer_stage1.cu); same int16 partial
 // planes as K1a.  Returns MULUT_OK, an error (< 0) or +1 (frames not TMA-mappable: run K1a).
+bool tma_mappable(const void *base, int H, int row_bytes);   // tma.cu: can a tensor map address these frames in place?
 bool stage1_tma_supported(const StageArgs &a, int up);
 size_t stage1_pair_bytes();
 int build_pair_table(const int8_t *d_lut_vertex_major, uint8_t *d_pair, cudaStream_t stream);

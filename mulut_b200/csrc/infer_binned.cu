@@ -401,9 +401,11 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
         // ---- scan: queue the samples of my bin (4 samples = one word per thread of the first 24 warps) ----
         if (tid < BN_SCAN_THREADS) {
             const uint32_t w = *reinterpret_cast<const uint32_t *>(tile + scan_off);
-            const bool valid = (info.y + srow < a.H) && (info.z + swc * 4 < WC);      // WC % 16 == 0: whole words
+            const int nv = WC - (info.z + swc * 4);                                   // samples of this word inside the frame
+            const bool valid = (info.y + srow < a.H) && nv > 0;
             const uint32_t x = ((w >> 5) & 0x07070707u) ^ bin_pat;                    // byte == 0  <=>  sample in my bin
             uint32_t m = valid ? (~(x + 0x7F7F7F7Fu) & 0x80808080u) : 0u;
+            if (nv < 4) m &= 0x80808080u >> (8 * (4 - max(nv, 1)));                   // a row that does not end on a word
             const uint32_t cnt = __popc(m);
             uint32_t incl = cnt;
 #pragma unroll
@@ -512,7 +514,7 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
 bool binned_supported(const StageArgs &a, int up)
 {
     return up == 2 && a.last && a.interval == 4 && a.n_modes >= 1 && a.n_modes <= BN_MAX_MODES &&
-           a.C >= 1 && a.C <= 4 && a.lut_slab[0] != nullptr && tma_frame_ok(a.in, a.H, a.W * a.C);
+           a.C >= 1 && a.C <= 4 && a.lut_slab[0] != nullptr;
 }
 
 template <int CT>
@@ -555,7 +557,8 @@ int launch_stage_binned(const StageArgs &a, void *ctl_mem, uint32_t *list, size_
     const size_t total = (size_t)a.N * a.H * a.W * a.C;
     if (total == 0) return MULUT_OK;
     CUtensorMap tmap;
-    if (tma_encode_frames(&tmap, a.in, a.N, a.H, a.W * a.C, BN_BOXW, BN_BOXH) != 0) return 1;   // caller falls back
+    if (!a.in_tma || tma_encode_frames(&tmap, a.in_tma, a.N, a.H, a.W * a.C, a.in_pitch, BN_BOXW, BN_BOXH) != 0)
+        return 1;                                          // caller falls back
     BinCtl *ctl = static_cast<BinCtl *>(ctl_mem);
     const BinPlanArgs pa = binned_plan_args(a, ctl_mem, list, list_cap);
     if (pa.n_tiles >= 0x7fffffffLL) return 1;              // 32-bit tile arithmetic and tile counters in the kernel

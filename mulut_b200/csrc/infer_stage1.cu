@@ -14,7 +14,8 @@
 //     fraction needs no masking), the vertex chain is v0, v0+s1, v0+s1+s2, v4-s4, v4 with
 //     v4 = v0 + 5220 (all four taps incremented) - three masks instead of four.
 //
-// TMA needs 16-byte aligned frames with W*C % 16 == 0; other shapes run K1a.
+// TMA needs 16-byte aligned frames with a row pitch that is a multiple of 16: other frames are
+// first copied into a pitched staging buffer (capi.cu: tma_view).
 // Arithmetic follows SURVEY.md 8-SPEC (sr/4_test_lut.py:14-237, :279-306).
 #include "common.cuh"
 #include "infer.cuh"
@@ -367,7 +368,7 @@ stage_pair_tma_kernel(const __grid_constant__ Stage1Args a, const __grid_constan
 bool stage1_tma_supported(const StageArgs &a, int up)
 {
     return up == 1 && a.interval == 4 && a.n_modes >= 1 && a.C >= 1 && a.C <= 4 && a.lut_alt[0] != nullptr &&
-           tma_frame_ok(a.in, a.H, a.W * a.C);
+           a.in_tma != nullptr;
 }
 
 template <int CT>
@@ -407,7 +408,7 @@ static int launch_stage1_t(Stage1Args &s, const CUtensorMap &tmap, int num_sms, 
 int launch_stage1_tma(const StageArgs &a, int16_t *partial, cudaStream_t stream)
 {
     CUtensorMap tmap;
-    if (tma_encode_frames(&tmap, a.in, a.N, a.H, a.W * a.C, G1_BOXW, G1_BOXH) != 0) return 1;
+    if (!a.in_tma || tma_encode_frames(&tmap, a.in_tma, a.N, a.H, a.W * a.C, a.in_pitch, G1_BOXW, G1_BOXH) != 0) return 1;
     Stage1Args s;
     memset(&s, 0, sizeof s);
     s.partial = partial; s.N = a.N; s.H = a.H; s.W = a.W; s.C = a.C; s.n_modes = a.n_modes;

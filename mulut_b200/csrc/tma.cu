@@ -24,12 +24,14 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn()
     return fn;
 }
 
-int tma_encode_frames(CUtensorMap *map, const void *base, int N, int H, int WC, int box_w, int box_h)
+bool tma_mappable(const void *base, int H, int row_bytes) { return tma_frame_ok(base, H, row_bytes); }
+
+int tma_encode_frames(CUtensorMap *map, const void *base, int N, int H, int WC, int pitch, int box_w, int box_h)
 {
     PFN_cuTensorMapEncodeTiled_v12000 fn = encode_fn();
-    if (!fn || !tma_frame_ok(base, H, WC) || N < 1) return 1;
+    if (!fn || !tma_frame_ok(base, H, pitch) || pitch < WC || N < 1) return 1;
     const cuuint64_t dims[3] = {(cuuint64_t)WC, (cuuint64_t)H, (cuuint64_t)N};
-    const cuuint64_t strides[2] = {(cuuint64_t)WC, (cuuint64_t)WC * (cuuint64_t)H};   // bytes, dims 1 and 2
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * (cuuint64_t)H};   // bytes, dims 1 and 2
     const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,

@@ -22,7 +22,8 @@ inline bool tma_frame_ok(const void *base, int H, int WC)
 }
 
 // Returns 0 on success.  box_w must be a multiple of 16 and <= 256, box_h <= 256.
-int tma_encode_frames(CUtensorMap *map, const void *base, int N, int H, int WC, int box_w, int box_h);
+// Frames of H rows of WC bytes, rows `pitch` bytes apart (pitch % 16 == 0, base 16-byte aligned).
+int tma_encode_frames(CUtensorMap *map, const void *base, int N, int H, int WC, int pitch, int box_w, int box_h);
 
 // ---------------------------------------------------------------------------
 // device: mbarrier + bulk copies (shared::cta addresses as 32-bit)

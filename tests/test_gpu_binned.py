@@ -1,8 +1,8 @@
 """K1f (binned shared-memory last stage, TMA tile ring) against the C oracle.
 
-The kernel needs TMA-mappable frames (16-byte aligned, W*C % 16 == 0, C in {1,3});
-every case here satisfies that and asserts through the per-kernel profile counters
-that K1f is the kernel that actually ran."""
+The kernel reads its tiles through TMA (16-byte aligned frames, row pitch a multiple of 16; other
+frames go through a pitched staging copy first); the cases assert through the per-kernel profile
+counters that K1f is the kernel that actually ran."""
 import numpy as np
 import pytest
 
@@ -84,19 +84,29 @@ def test_binned_mode_subsets_and_stages(modes, stages, monkeypatch):
     assert (out == ref).all(), (modes, stages, int((out != ref).sum()))
 
 
-def test_binned_falls_back_when_tma_cannot_map_the_frame():
-    """W*C % 16 != 0: the forced binned selection runs K1c instead (still bit-exact)."""
+def test_unmappable_frames_go_through_the_pitched_copy():
+    """W*C % 16 != 0 or a misaligned device pointer: TMA cannot map the frames in place, so the stage input
+    is first copied into a pitched staging buffer - the TMA-fed kernels still run, still bit-exact."""
     import torch
     from mulut_b200.infer import LutEngine
     rng = np.random.default_rng(3)
     luts = O.random_luts(4, 2, "sdy", 2)
-    img = rng.integers(0, 256, (41, 37, 3), dtype=np.uint8)
-    with LutEngine(luts, 2, "sdy", 2, 4, device=0, kernel=3) as eng:
-        eng.profile(True)
-        out = eng(torch.from_numpy(img).cuda()).cpu().numpy()
-        prof = eng.profile_read()
-    assert "last_tiled" in prof and "last_binned" not in prof
-    assert (out == CO.sr_u8(img, luts, 2, "sdy", 2)).all()
+    for shape in [(41, 37, 3), (2, 33, 50, 1), (3, 70, 21, 4), (1, 19, 3, 2), (1, 40, 64, 3)]:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        ref = CO.sr_u8(img, luts, 2, "sdy", 2)
+        with LutEngine(luts, 2, "sdy", 2, 4, device=0, kernel=3) as eng:
+            eng.profile(True)
+            out = eng(torch.from_numpy(img).cuda()).cpu().numpy()
+            prof = eng.profile_read()
+            assert "last_binned" in prof and "last_tiled" not in prof, (shape, list(prof))
+            assert (out == ref).all(), shape
+            # the same frames at an address that is not 16-byte aligned
+            buf = torch.empty(img.size + 64, dtype=torch.uint8, device="cuda")
+            off = 16 - buf.data_ptr() % 16 + 5
+            view = buf[off:off + img.size].view(*img.shape)
+            view.copy_(torch.from_numpy(img))
+            assert view.data_ptr() % 16 == 5
+            assert (eng(view).cpu().numpy() == ref).all(), shape
 
 
 def test_orphan_list_gets_the_sparse_bins():
