@@ -425,8 +425,19 @@ int mulut_reserve(mulut_handle_t h, int N, int H, int W, int C)
     int rc = check_shape(h, (void *)1, (void *)1, N, H, W, C);
     if (rc) return rc;
     MULUT_CUDA(cudaSetDevice(h->device));
-    return ws_reserve(h->ws[0], h->stages, h->n_modes, (size_t)N * H * W * C, h->interval == 4,
-                      h->scale == 2 && h->interval == 4);
+    rc = ws_reserve(h->ws[0], h->stages, h->n_modes, (size_t)N * H * W * C, h->interval == 4,
+                    h->scale == 2 && h->interval == 4);
+    if (rc) return rc;
+    // the pitched staging copy of frames TMA cannot map in place (sized for the worst case: the caller's
+    // pointer may turn out to be misaligned even when W*C is a multiple of 16)
+    Workspace &w = h->ws[0];
+    const size_t need = (size_t)N * H * (((size_t)W * C + 15) / 16 * 16);
+    if (h->interval == 4 && C <= 4 && w.pitched_bytes < need) {
+        cudaFree(w.pitched); w.pitched = nullptr; w.pitched_bytes = 0;
+        MULUT_CUDA(cudaMalloc(&w.pitched, need));
+        w.pitched_bytes = need;
+    }
+    return MULUT_OK;
 }
 
 int mulut_sr_infer_u8(mulut_handle_t h, const uint8_t *d_in, uint8_t *d_out, int N, int H, int W, int C,

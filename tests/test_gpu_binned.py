@@ -215,3 +215,31 @@ def test_binned_randomised_shapes_and_distributions(seed, monkeypatch):
     with LutEngine(luts, stages, "sdy", 2, 4, device=0, kernel=3) as eng:
         out = _run(eng, img)
     assert (out == ref).all(), (seed, img.shape, stages, int((out != ref).sum()))
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 96, 3), (1, 41, 37, 3)])
+def test_device_path_is_cuda_graph_capturable_after_reserve(shape):
+    """mulut_reserve pre-sizes every buffer the hot call needs (including the pitched staging copy of frames
+    TMA cannot map in place), so mulut_sr_infer_u8 can be captured into a CUDA graph and replayed on new frames."""
+    import torch
+    from mulut_b200.infer import LutEngine
+    rng = np.random.default_rng(21)
+    luts = O.random_luts(31, 2, "sdy", 2)
+    N, H, W, C = shape
+    with LutEngine(luts, 2, "sdy", 2, 4, device=0, kernel=3) as eng:
+        eng.reserve(N, H, W, C)
+        d_in = torch.zeros(shape, dtype=torch.uint8, device="cuda")
+        d_out = torch.empty((N, 2 * H, 2 * W, C), dtype=torch.uint8, device="cuda")
+        side = torch.cuda.Stream()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            eng.infer_device(d_in, d_out)                  # warm-up outside the capture
+            side.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                eng.infer_device(d_in, d_out)
+        for seed in range(3):
+            frames = rng.integers(0, 256, shape, dtype=np.uint8)
+            d_in.copy_(torch.from_numpy(frames))
+            graph.replay()
+            torch.cuda.synchronize()
+            assert (d_out.cpu().numpy() == CO.sr_u8(frames, luts, 2, "sdy", 2)).all(), (shape, seed)
