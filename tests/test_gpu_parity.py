@@ -100,6 +100,13 @@ def test_streaming_host_path_overlapping_calls(kernel):
         for fr, out in jobs:
             assert (out == CO.sr_u8(np.asarray(fr), luts, 2, "sdy", 2)).all()
         eng.host_sync()                                   # idempotent
+        # pageable (plain numpy) buffers work too, only slower: results are complete after host_sync
+        fr = rng.integers(0, 256, (3, 70, 112, 3), dtype=np.uint8)
+        out = np.zeros((3, 140, 224, 3), dtype=np.uint8)
+        eng.infer_host_async(fr, out)
+        eng.infer_host_async(jobs[0][0], jobs[0][1])
+        eng.host_sync()
+        assert (out == CO.sr_u8(fr, luts, 2, "sdy", 2)).all()
         with pytest.raises(ValueError):
             eng.infer_host_async(jobs[0][0], jobs[1][1])  # wrong out shape
 
