@@ -122,7 +122,10 @@ def main():
            "n_gpus": world, "ms_per_step": float(t.item()) * 1e3, "patches_per_s": args.batch / float(t.item()),
            "mode": "eager" if args.eager else "cuda graph",
            "breakdown_ms": {k: v / args.steps for k, v in timers.items()} if args.eager else None, "loss": float(loss.item()),
-           "allreduce_bytes": bucket.flat.numel() * 4}
+           "allreduce_bytes": bucket.flat.numel() * 4,
+           # 60 + 960 fp32 scatter-adds per patch pixel in the backward (issued as 60 scalar + 240 four-wide reds)
+           "lut_grad_scatter_adds_per_step": args.batch * args.crop * args.crop * 1020,
+           "scatter_adds_per_s": args.batch * args.crop * args.crop * 1020 / float(t.item())}
 
     if rank == 0:
         print(json.dumps(res), flush=True)
