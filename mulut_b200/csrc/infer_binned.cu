@@ -268,7 +268,9 @@ __device__ unsigned long long g_bn_timing[256 * 8];
 #define BN_TEND() do {} while (0)
 #endif
 
-template <int CT>
+// SDY: the model's modes are exactly "sdy" (the shipped configuration): the three mode bodies run back to back
+// with no per-sample dispatch and share the tap loads they have in common
+template <int CT, bool SDY>
 __global__ void __launch_bounds__(BN_THREADS, 1)
 stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_constant__ CUtensorMap tmap)
 {
@@ -464,12 +466,19 @@ stage_last2_binned_kernel(const __grid_constant__ BinnedArgs a, const __grid_con
                 const int a_rel = (int)(t0 >> 4) - 2 * bin;
                 uint32_t AE[4] = {0u, 0u, 0u, 0u};
                 unsigned long long AO[4] = {0ull, 0ull, 0ull, 0ull};
-                for (int m = 0; m < a.n_modes; ++m) {
-                    const uint8_t *lut_a = s_lut + m * BN_BIN_BYTES + a_rel * BN_SLAB_BYTES;
-                    switch (a.modes[m]) {
-                    case 's': binned_mode<'s', CT>(sp, t0, lut_a, AE, AO); break;
-                    case 'd': binned_mode<'d', CT>(sp, t0, lut_a, AE, AO); break;
-                    default: binned_mode<'y', CT>(sp, t0, lut_a, AE, AO); break;
+                if (SDY) {
+                    const uint8_t *lut_a = s_lut + a_rel * BN_SLAB_BYTES;
+                    binned_mode<'s', CT>(sp, t0, lut_a, AE, AO);
+                    binned_mode<'d', CT>(sp, t0, lut_a + BN_BIN_BYTES, AE, AO);
+                    binned_mode<'y', CT>(sp, t0, lut_a + 2 * BN_BIN_BYTES, AE, AO);
+                } else {
+                    for (int m = 0; m < a.n_modes; ++m) {
+                        const uint8_t *lut_a = s_lut + m * BN_BIN_BYTES + a_rel * BN_SLAB_BYTES;
+                        switch (a.modes[m]) {
+                        case 's': binned_mode<'s', CT>(sp, t0, lut_a, AE, AO); break;
+                        case 'd': binned_mode<'d', CT>(sp, t0, lut_a, AE, AO); break;
+                        default: binned_mode<'y', CT>(sp, t0, lut_a, AE, AO); break;
+                        }
                     }
                 }
                 // fields: AE = S0 | S2<<16;  AO - AE = S1<<8 | S3<<24 (S_j < 2^16: 12 interp x 16 x 255)
@@ -517,15 +526,22 @@ bool binned_supported(const StageArgs &a, int up)
            a.C >= 1 && a.C <= 4 && a.lut_slab[0] != nullptr;
 }
 
+template <int CT, bool SDY>
+static int launch_binned_ts(const BinnedArgs &b, const CUtensorMap &tmap, int num_sms, cudaStream_t stream)
+{
+    // per device and cheap: set on every launch (one process may own several devices)
+    MULUT_CUDA(cudaFuncSetAttribute(stage_last2_binned_kernel<CT, SDY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)BN_SMEM));
+    stage_last2_binned_kernel<CT, SDY><<<num_sms, BN_THREADS, BN_SMEM, stream>>>(b, tmap);
+    MULUT_CUDA(cudaGetLastError());
+    return MULUT_OK;
+}
+
 template <int CT>
 static int launch_binned_t(const BinnedArgs &b, const CUtensorMap &tmap, int num_sms, cudaStream_t stream)
 {
-    // per device and cheap: set on every launch (one process may own several devices)
-    MULUT_CUDA(cudaFuncSetAttribute(stage_last2_binned_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)BN_SMEM));
-    stage_last2_binned_kernel<CT><<<num_sms, BN_THREADS, BN_SMEM, stream>>>(b, tmap);
-    MULUT_CUDA(cudaGetLastError());
-    return MULUT_OK;
+    const bool sdy = b.n_modes == 3 && b.modes[0] == 's' && b.modes[1] == 'd' && b.modes[2] == 'y';
+    return sdy ? launch_binned_ts<CT, true>(b, tmap, num_sms, stream) : launch_binned_ts<CT, false>(b, tmap, num_sms, stream);
 }
 
 int launch_stage_generic_list2(const StageArgs &a, const uint32_t *list, const uint32_t *count, cudaStream_t stream);
