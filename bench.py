@@ -331,6 +331,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_sync_value = out_pix_per_step * args.steps / float(t.item()) / 1e6
+    sync_out = np.array(host_out) if rank == 0 else None       # kept for the parity check (the streaming leg reuses host_out)
     # (b) the streaming form (a video pipeline): the same steps enqueued back to back, outputs alternating
     # between two pinned buffers, one wait at the end - every step's H2D and D2H is still inside the region
     host_out2 = pinned_empty(host_out.shape)
@@ -348,9 +349,29 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = out_pix_per_step * args.steps / float(t.item()) / 1e6
-    if not np.array_equal(host_out2[-1, ::97, ::89], host_out[-1, ::97, ::89]):
+    if not np.array_equal(host_out2, host_out):
         raise SystemExit("streaming host path: the two output buffers differ")
     sanity = int(host_out[0, :8, :8].sum())    # device->host read of the step's result
+
+    # ---------------- parity of what was timed (outside every timed region) ----------------
+    # One whole frame of each timed leg - device-resident, blocking host call, streaming host call - against
+    # the C oracle (the checker; oracle/mulut_oracle.c) on the same input frame; all frames of the legs must
+    # also agree with each other byte for byte.  A mismatch fails the run.
+    parity = None
+    if rank == 0:
+        from oracle import c_oracle as CO
+        dev_out = d_out.cpu().numpy()
+        ref0 = CO.sr_u8(np.asarray(host_in[:1]), luts, STAGES, MODES, SCALE, INTERVAL, 0)
+        legs = {"device": dev_out, "host_sync": sync_out, "host_async": host_out, "host_async (second buffer)": host_out2}
+        for name, arr in legs.items():
+            if not np.array_equal(arr[0], ref0[0]):
+                raise SystemExit("PARITY FAILURE: leg '{}' differs from the C oracle in {} bytes".format(
+                    name, int((arr[0] != ref0[0]).sum())))
+            if not np.array_equal(arr, dev_out):
+                raise SystemExit("PARITY FAILURE: leg '{}' differs from the device leg".format(name))
+        parity = {"result": "bit-exact", "checked": "frame 0 of the device, host_sync and host_async legs vs the C oracle "
+                  "({} bytes each); all {} frames of the three legs identical".format(ref0[0].size, F)}
+        del dev_out, sync_out
 
     # ---------------- the same step on natural-like frames (reported beside the headline) ----------------
     natural = None
@@ -481,6 +502,7 @@ def main():
                 "sync_per_step": {"value": e2e_sync_value, "unit": "Mpix/s", "api": "LutEngine.infer_host -> mulut_sr_infer_u8_host, one blocking call per step"},
                 "host_memory": "pinned", "check": sanity},
         "gpu_launches": int(launches) * world,
+        "parity": parity,
         "clocks": clocks,
         "roofline": roofline,
         "gather_roofline": gather_roofline,

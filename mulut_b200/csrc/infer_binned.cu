@@ -52,7 +52,7 @@ constexpr int BN_HX = 16;                       // box column of the tile's firs
                                                 // is fetched as a whole 16-byte granule
 constexpr int BN_BOXW = 128;                    // HX + TW + 2*C rounded up to 16 B (C <= 4)
 constexpr int BN_BOXH = BN_TH + 4;
-constexpr int BN_SLOT = BN_BOXW * BN_BOXH;      // 4608 B per ring slot, 128-B aligned
+constexpr int BN_SLOT = BN_BOXW * BN_BOXH;      // 2560 B per ring slot, 128-B aligned
 constexpr int BN_RING = 6;
 constexpr int BN_AHEAD = 2;                     // TMA prefetch distance in tiles
 constexpr int BN_CARRY = BN_RING - BN_AHEAD - 1;   // tiles a queue entry may outlive its scan
@@ -578,6 +578,10 @@ int launch_stage_binned(const StageArgs &a, void *ctl_mem, uint32_t *list, size_
     BinCtl *ctl = static_cast<BinCtl *>(ctl_mem);
     const BinPlanArgs pa = binned_plan_args(a, ctl_mem, list, list_cap);
     if (pa.n_tiles >= 0x7fffffffLL) return 1;              // 32-bit tile arithmetic and tile counters in the kernel
+    // the histogram and the orphan scan read the DENSE stage input with 16-byte loads (the orphan list holds
+    // dense indices, so the pitched copy cannot stand in): a misaligned caller pointer - only possible for a
+    // single-stage model, every later stage reads the workspace - goes to K1c
+    if (reinterpret_cast<uintptr_t>(a.in) & 15u) return 1;
     BinnedArgs b;
     memset(&b, 0, sizeof b);
     b.out = a.out; b.N = a.N; b.H = a.H; b.W = a.W; b.C = a.C; b.n_modes = a.n_modes; b.ctl = ctl;

@@ -38,6 +38,31 @@ def set5():
     print("set5_x4.npz", {k: v.shape for k, v in d.items()})
 
 
+def set5_hr_metrics():
+    """The five Set5 HR images (decoded) and the report numbers the reference's OWN evaluation code
+    (common/utils.py:28-101 modcrop, _rgb2ycbcr, PSNR, cal_ssim, called as eltr._worker does,
+    sr/4_test_lut.py:273-314) gives for its golden results: the known answer of sr/4_test_lut.py:343."""
+    from PIL import Image
+    utils = R.utils_module()
+    names = ["baby", "bird", "butterfly", "head", "woman"]
+    d, rows = {}, {}
+    for n in names:
+        hr = np.array(Image.open(os.path.join(R.REF_ROOT, "data/SRBenchmark/Set5/HR", n + ".png")))
+        sr = np.array(Image.open(os.path.join(R.REF_ROOT, "results/sr_x2sdy/Set5/X4", n + "_LUT_ft_4bit.png")))
+        d["hr_" + n] = hr
+        gt = utils.modcrop(hr, 4)
+        y_gt, y_out = utils._rgb2ycbcr(gt)[:, :, 0], utils._rgb2ycbcr(sr)[:, :, 0]
+        rows[n] = {"psnr": float(utils.PSNR(y_gt, y_out, 4)), "ssim": float(utils.cal_ssim(y_gt, y_out)),
+                   "y_gt_sum": float(y_gt.sum()), "y_out_sum": float(y_out.sum())}
+    rows["_mean"] = {"psnr": float(np.mean([rows[n]["psnr"] for n in names])),
+                     "ssim": float(np.mean([rows[n]["ssim"] for n in names]))}
+    rows["_printed"] = "Dataset Set5 | AVG LUT PSNR: {:.2f} SSIM: {:.4f}".format(rows["_mean"]["psnr"], rows["_mean"]["ssim"])
+    np.savez_compressed(os.path.join(GOLD, "set5_hr.npz"), **d)
+    with open(os.path.join(GOLD, "set5_metrics.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+    print("set5_hr.npz / set5_metrics.json:", rows["_printed"])
+
+
 def shipped_luts():
     out = os.path.join(GOLD, "luts_x4")
     os.makedirs(out, exist_ok=True)
@@ -196,6 +221,7 @@ def main():
         raise SystemExit("reference tree not found at " + R.REF_ROOT)
     os.makedirs(GOLD, exist_ok=True)
     set5()
+    set5_hr_metrics()
     shipped_luts()
     pipeline_cases()
     pass_cases()

@@ -54,6 +54,11 @@ def model_module():
     return _load("ref_sr_model", os.path.join(REF_ROOT, "sr", "model.py"))
 
 
+def utils_module():
+    """common/utils.py (modcrop, _rgb2ycbcr, PSNR, cal_ssim: the reference's report metrics)."""
+    return _load("ref_common_utils", os.path.join(REF_ROOT, "common", "utils.py"))
+
+
 def transfer_module():
     """sr/2_transfer_to_lut.py (the LUT producer; only its grid-enumeration helpers are used)."""
     return _load("ref_2_transfer_to_lut", os.path.join(REF_ROOT, "sr", "2_transfer_to_lut.py"))

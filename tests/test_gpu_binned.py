@@ -109,6 +109,34 @@ def test_unmappable_frames_go_through_the_pitched_copy():
             assert (eng(view).cpu().numpy() == ref).all(), shape
 
 
+@pytest.mark.parametrize("kernel", [3, -1])
+def test_single_stage_model_with_a_misaligned_input_pointer(kernel):
+    """A ONE-stage x2 model reads the caller's pointer in its last stage: K1f's histogram and orphan scan use
+    16-byte loads on the dense input, so a misaligned pointer must not reach them (it takes K1c instead of
+    faulting); forced (kernel 3) and through AUTO at >= 2^20 samples."""
+    import torch
+    from mulut_b200.infer import LutEngine
+    rng = np.random.default_rng(21)
+    luts = O.random_luts(22, 1, "sdy", 2)
+    img = rng.integers(0, 256, (2, 384, 480, 3), dtype=np.uint8)          # 1.1 M samples, W*C % 16 == 0
+    img[0, :200] = rng.integers(100, 140, (200, 480, 3))                   # some sparse bins as well
+    ref = CO.sr_u8(img, luts, 1, "sdy", 2)
+    with LutEngine(luts, 1, "sdy", 2, 4, device=0, kernel=kernel) as eng:
+        for misalign in (0, 1, 5, 8):
+            buf = torch.empty(img.size + 64, dtype=torch.uint8, device="cuda")
+            off = (16 - buf.data_ptr() % 16) % 16 + misalign
+            view = buf[off:off + img.size].view(*img.shape)
+            view.copy_(torch.from_numpy(img))
+            assert view.data_ptr() % 16 == misalign
+            eng.profile(True)
+            out = eng(view).cpu().numpy()
+            prof = eng.profile_read()
+            eng.profile(False)
+            torch.cuda.synchronize()
+            assert (out == ref).all(), (kernel, misalign, int((out != ref).sum()))
+            assert ("last_binned" in prof) == (misalign == 0), (misalign, list(prof))
+
+
 def test_orphan_list_gets_the_sparse_bins():
     """A frame whose values sit in two bins plus a sprinkle elsewhere: the sprinkle must go
     through the orphan list kernel, the two dense bins through shared memory."""

@@ -1,6 +1,7 @@
-"""On-device PSNR / SSIM (mulut_eval_psnr_ssim_y_u8) against the host definitions in
-mulut_b200.metrics, which mirror the reference's common/utils.py:42-101 (checked against the
-reference itself by the CPU suite when /root/reference is present)."""
+"""On-device PSNR / SSIM (mulut_eval_psnr_ssim_y_u8) on synthetic and ragged images against the host
+definitions in mulut_b200.metrics.  Those host definitions - and the device kernel itself - are pinned to
+the reference's common/utils.py:42-101 by tests/test_metrics_pinned.py (reference-computed Set5 numbers,
+plus a live comparison when /root/reference is present)."""
 import numpy as np
 import pytest
 

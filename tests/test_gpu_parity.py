@@ -188,6 +188,59 @@ def test_full_size_properties_x4_960x540(shipped_luts):
     assert (spot[:-16, :-16] == ot[0, :256 - 16, :256 - 16]).all()
 
 
+def test_full_size_x4_960x540_matches_c_oracle(shipped_luts):
+    """BASELINE config 3 at full size: one 960x540 RGB frame -> 4K with the reference's shipped x4 LUTs,
+    bit-exact against the C oracle for AUTO and for every kernel family."""
+    import torch
+    from mulut_b200.infer import LutEngine
+    rng = np.random.default_rng(33)
+    frame = rng.integers(0, 256, (1, 540, 960, 3), dtype=np.uint8)
+    ref = CO.sr_u8(frame, shipped_luts, 2, "sdy", 4)
+    assert ref.shape == (1, 2160, 3840, 3)
+    d = torch.from_numpy(frame).cuda()
+    for kernel in [-1] + sorted(set(KERNELS.values())):
+        with LutEngine(shipped_luts, 2, "sdy", 4, 4, device=0, kernel=kernel) as eng:
+            out = eng(d).cpu().numpy()
+        assert (out == ref).all(), (kernel, int((out != ref).sum()))
+
+
+def test_full_size_8k_x2_matches_c_oracle():
+    """BASELINE config 5 at full size: one 7680x4320 RGB frame -> 15360x8640 (398 MB), AUTO policy,
+    bit-exact against the C oracle; also through the host path."""
+    import torch
+    from mulut_b200.infer import LutEngine, pinned_empty
+    rng = np.random.default_rng(55)
+    luts = O.random_luts(1, 2, "sdy", 2)
+    frame = rng.integers(0, 256, (1, 4320, 7680, 3), dtype=np.uint8)
+    ref = CO.sr_u8(frame, luts, 2, "sdy", 2)
+    with LutEngine(luts, 2, "sdy", 2, 4, device=0) as eng:
+        eng.profile(True)
+        out = eng(torch.from_numpy(frame).cuda()).cpu().numpy()
+        prof = eng.profile_read()
+        eng.profile(False)
+        assert "last_binned" in prof and "smem_stage" in prof, prof      # AUTO took the TMA-fed kernels
+        assert out.shape == (1, 8640, 15360, 3)
+        assert (out == ref).all(), int((out != ref).sum())
+        del out
+        hout = pinned_empty(ref.shape)
+        eng.infer_host(frame, hout)
+        assert (hout == ref).all()
+
+
+def test_cfg1_batch_of_64_256x256_x4_matches_c_oracle(shipped_luts):
+    """BASELINE config 1 (the reference's CPU-runnable case) as bench.py times it: a 64-frame batch of
+    256x256 RGB frames, shipped x4 LUTs, AUTO policy."""
+    import torch
+    from mulut_b200.infer import LutEngine
+    rng = np.random.default_rng(11)
+    frames = rng.integers(0, 256, (64, 256, 256, 3), dtype=np.uint8)
+    ref = CO.sr_u8(frames, shipped_luts, 2, "sdy", 4)
+    with LutEngine(shipped_luts, 2, "sdy", 4, 4, device=0) as eng:
+        out = eng(torch.from_numpy(frames).cuda()).cpu().numpy()
+        assert (out == ref).all(), int((out != ref).sum())
+        assert (eng(frames) == ref).all()
+
+
 def test_call_compatible_single_pass(pass_cases):
     from mulut_b200.infer import FourSimplexInterpFaster
     meta, data = pass_cases
@@ -216,25 +269,3 @@ def test_error_mapping():
         assert out.shape == (0, 16, 16, 3)
         g = eng(np.random.default_rng(0).integers(0, 256, (6, 7), dtype=np.uint8))   # grey -> 3 channels
         assert g.shape == (12, 14, 3) and (g[..., 0] == g[..., 1]).all()
-
-
-def test_cli_reproduces_set5_numbers(tmp_path, set5, shipped_luts, gold_dir):
-    """4_test_lut.py flags end to end on a Set5-shaped tree built from the fixtures
-    (HR = the golden SR images, so PSNR is inf-free only for the file checks)."""
-    import os
-    from PIL import Image
-    from mulut_b200.cli import test_lut
-    root = tmp_path / "data" / "Set5"
-    (root / "HR").mkdir(parents=True)
-    (root / "LR_bicubic" / "X4").mkdir(parents=True)
-    for n in NAMES:
-        Image.fromarray(set5["lr_" + n]).save(root / "LR_bicubic" / "X4" / (n + ".png"))
-        hr = set5["sr_" + n].copy()
-        hr[0, 0, 0] ^= 1                      # avoid rmse == 0
-        Image.fromarray(hr).save(root / "HR" / (n + ".png"))
-    res = test_lut.main(["--stages", "2", "--modes", "sdy", "-e", os.path.join(gold_dir, "luts_x4"),
-                         "--testDir", str(tmp_path / "data"), "--resultRoot", str(tmp_path / "results")])
-    for n in NAMES:
-        got = np.array(Image.open(tmp_path / "results" / "luts_x4" / "Set5" / "X4" / (n + "_LUT_ft_4bit.png")))
-        assert (got == set5["sr_" + n]).all(), n
-    assert res["Set5"].shape == (5, 2)
