@@ -154,18 +154,21 @@ def measured_peaks():
 
 
 def gather_peak(device):
-    """Measured denominators of the gather roofline (GB/s of 32-byte sectors that
-    L2 can deliver to the SMs under random cell fetches), live, ~0.2 s."""
+    """Measured denominators of the gather roofline (mulut_gather_bench, live, ~0.5 s): independent random
+    gathers of one shape from one memory level on all SMs.  ONE fixed peak per primitive: the best of the
+    launch shapes tried (not the shape of the kernel that is compared with it)."""
     from mulut_b200 import _lib
     L = _lib.lib()
     out = (ctypes.c_double * 3)()
     res = {}
-    for name, table, bps, tpb in [("quad_cell64", 12 << 20, 4, 512), ("ldg_u32", 1 << 20, 4, 512),
-                                  ("lds_u8", 83584, 2, 512), ("lds_u32", 176976, 1, 768),
-                                  ("quad_cell256_3rows", 50 << 20, 2, 384)]:
-        rc = L.mulut_gather_bench(device, _lib.GB_VARIANTS[name], table, 256, bps, tpb, 3, out)
-        if rc == 0:
-            res[name] = {"gathers_per_s": out[0], "useful_GBps": out[1] / 1e9}
+    for name, table, shapes in [("quad_cell64", 12 << 20, [(4, 512)]), ("ldg_u32", 1 << 20, [(4, 512)]),
+                                ("lds_u8", 83584, [(2, 512), (1, 1024), (2, 384)]),
+                                ("lds_u32", 176976, [(1, 768), (1, 1024)]),
+                                ("quad_cell256_3rows", 50 << 20, [(2, 384)])]:
+        for bps, tpb in shapes:
+            rc = L.mulut_gather_bench(device, _lib.GB_VARIANTS[name], table, 256, bps, tpb, 3, out)
+            if rc == 0 and out[0] > res.get(name, {}).get("gathers_per_s", 0.0):
+                res[name] = {"gathers_per_s": out[0], "useful_GBps": out[1] / 1e9, "blocks_per_sm": bps, "threads": tpb}
     return res
 
 
@@ -184,6 +187,60 @@ def cpu_port_throughput(min_seconds, max_frames, threads=0):
             break
     cores = threads if threads > 0 else CO.max_threads()
     return n * H * W * SCALE * SCALE / dt / 1e6, cores, n, dt
+
+
+def _numpy_ref_worker(job):
+    """One pool worker = one 256x256 frame through the UNMODIFIED reference numpy path: the reference's own
+    FourSimplexInterpFaster (sr/4_test_lut.py:14-237) driven by its _worker loop (:279-306, restated in
+    oracle/ref_import.ref_pipeline), single-threaded like the reference's Pool workers (:257-259)."""
+    cfg, seed, idx = job
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = "1"
+    select_config(cfg)
+    from oracle import ref_import as R
+    R.test_lut_module()                                      # import outside the timed part
+    luts = make_luts()
+    img = np.random.default_rng(seed + idx).integers(0, 256, (256, 256, C), dtype=np.uint8)
+    t0 = time.perf_counter()
+    out = R.ref_pipeline(img, luts, STAGES, list(MODES), SCALE, INTERVAL)
+    dt = time.perf_counter() - t0
+    return dt, (img, out) if idx == 0 else None
+
+
+def numpy_reference_throughput(cfg, max_workers=0):
+    """cpu_baseline.numpy_ref: the reference's numpy CPU path on this host, the reference's way - a
+    multiprocessing.Pool with one 256x256 frame (BASELINE config 1's frame size) per worker, one worker per
+    host core.  Cost per pixel does not depend on the frame size (every pass is elementwise over the
+    pixels), so Mpix/s carries over to 1080p frames linearly; a 1080p frame would need ~460 s and 2.9 GB
+    per worker."""
+    import multiprocessing as mp
+    from oracle import ref_import as R
+    if not R.available():
+        return {"unavailable": "oracle/_ref not staged (python -m oracle.fetch_ref in the build container)"}
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    if max_workers > 0:
+        cores = min(cores, max_workers)
+    ctx = mp.get_context("spawn")                            # this process holds a CUDA context: no fork
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_numpy_ref_worker, [(cfg, 4242, i) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    per_frame = [r[0] for r in res]
+    busy = max(per_frame)                                    # all workers start together: the slowest one bounds the batch
+    img, out = res[0][1]
+    from oracle import c_oracle as CO
+    same = bool(np.array_equal(CO.sr_u8(img, make_luts(), STAGES, MODES, SCALE, INTERVAL, 1), out))
+    pix = 256 * 256 * SCALE * SCALE
+    return {"value": cores * pix / busy / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "reference",
+            "per_core_Mpix_s": pix / (sum(per_frame) / len(per_frame)) / 1e6,
+            "sample": "{} x one 256x256x3 frame (scale {}), one per core under multiprocessing.Pool({}), slowest worker {:.1f} s "
+                      "(pool wall {:.1f} s incl. spawn + imports); unmodified reference FourSimplexInterpFaster from "
+                      "oracle/_ref".format(cores, SCALE, cores, busy, wall),
+            "scaling_note": "per-pixel cost is frame-size independent: carries over to 1080p linearly",
+            "c_oracle_agrees_on_this_frame": same}
 
 
 def run_reference_arm(args, rank, world):
@@ -230,6 +287,9 @@ def main():
                     help="synthetic frame content: i.i.d. uniform bytes (default, worst case) or tiled natural crops")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-finetune", action="store_true", help="skip the cfg4 finetune block")
+    ap.add_argument("--no-numpy-ref", action="store_true", help="skip cpu_baseline.numpy_ref (the reference's numpy path under a Pool)")
+    ap.add_argument("--finetune-steps", type=int, default=30)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     global DATA
@@ -276,12 +336,29 @@ def main():
     luts = make_luts()
     eng = LutEngine(luts, STAGES, MODES, SCALE, INTERVAL, device=local, kernel=kernel)
     F = args.frames
-    host_in = pinned_empty((F, H, W, C))
-    host_in[...] = make_frames(F, seed=1000 + rank)
-    host_out = pinned_empty((F, H * SCALE, W * SCALE, C))
+    # cfg5 on several GPUs: ONE stream of huge frames, every frame strip-sharded over the ranks with a
+    # 2-rows-per-stage halo (LutEngine.infer_strip's arithmetic) - total work fixed ("strong").
+    # Every other config shards whole frames: each rank has its own F frames ("weak").
+    strip = args.config == "cfg5" and world > 1
+    H_full = H
+    row_b, row_e, load_b, load_e = 0, H, 0, H
+    if strip:
+        from mulut_b200.dist import shard_rows_with_halo
+        row_b, row_e, load_b, load_e = shard_rows_with_halo(H_full, rank, world, 2 * STAGES)
+    HL = load_e - load_b                                     # input rows this rank reads
+    host_in = pinned_empty((F, HL, W, C))
+    if strip:
+        whole = make_frames(F, seed=1000)                    # the same frames on every rank
+        host_in[...] = whole[:, load_b:load_e]
+        frame0_whole = whole[:1].copy() if rank == 0 else None
+        del whole
+    else:
+        host_in[...] = make_frames(F, seed=1000 + rank)
+    host_out = pinned_empty((F, HL * SCALE, W * SCALE, C))
+    H_eff = HL                                               # the H the engine sees
     d_in = torch.from_numpy(np.ascontiguousarray(host_in)).cuda()
-    d_out = torch.empty((F, H * SCALE, W * SCALE, C), dtype=torch.uint8, device="cuda")
-    eng.reserve(F, H, W, C)
+    d_out = torch.empty((F, HL * SCALE, W * SCALE, C), dtype=torch.uint8, device="cuda")
+    eng.reserve(F, HL, W, C)
 
     def barrier():
         torch.cuda.synchronize()
@@ -314,7 +391,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    out_pix_per_step = world * F * H * W * SCALE * SCALE
+    out_pix_per_step = (1 if strip else world) * F * H_full * W * SCALE * SCALE
     value = out_pix_per_step * args.steps / (ms_max * 1e-3) / 1e6
 
     # ---------------- end-to-end leg: host buffers through the C ABI ----------------
@@ -349,7 +426,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = out_pix_per_step * args.steps / float(t.item()) / 1e6
-    if not np.array_equal(host_out2, host_out):
+    if rank == 0 and not np.array_equal(host_out2, host_out):
         raise SystemExit("streaming host path: the two output buffers differ")
     sanity = int(host_out[0, :8, :8].sum())    # device->host read of the step's result
 
@@ -361,17 +438,39 @@ def main():
     if rank == 0:
         from oracle import c_oracle as CO
         dev_out = d_out.cpu().numpy()
-        ref0 = CO.sr_u8(np.asarray(host_in[:1]), luts, STAGES, MODES, SCALE, INTERVAL, 0)
+        if strip:      # the whole frame through the oracle; this rank's strip is rows [row_b, row_e) of it
+            ref0 = CO.sr_u8(frame0_whole, luts, STAGES, MODES, SCALE, INTERVAL, 0)[:, row_b * SCALE:row_e * SCALE]
+            k0, k1 = (row_b - load_b) * SCALE, (row_e - load_b) * SCALE
+        else:
+            ref0 = CO.sr_u8(np.asarray(host_in[:1]), luts, STAGES, MODES, SCALE, INTERVAL, 0)
+            k0, k1 = 0, HL * SCALE
         legs = {"device": dev_out, "host_sync": sync_out, "host_async": host_out, "host_async (second buffer)": host_out2}
         for name, arr in legs.items():
-            if not np.array_equal(arr[0], ref0[0]):
+            if not np.array_equal(arr[0, k0:k1], ref0[0]):
                 raise SystemExit("PARITY FAILURE: leg '{}' differs from the C oracle in {} bytes".format(
-                    name, int((arr[0] != ref0[0]).sum())))
+                    name, int((arr[0, k0:k1] != ref0[0]).sum())))
             if not np.array_equal(arr, dev_out):
                 raise SystemExit("PARITY FAILURE: leg '{}' differs from the device leg".format(name))
         parity = {"result": "bit-exact", "checked": "frame 0 of the device, host_sync and host_async legs vs the C oracle "
                   "({} bytes each); all {} frames of the three legs identical".format(ref0[0].size, F)}
         del dev_out, sync_out
+
+    # ---------------- (c) the copy ceiling (after the parity check: it leaves stale bytes in the host buffers):
+    # the SAME copies on the same lanes (per frame one cudaMemcpyAsync in, one out) with no kernels between
+    # them - what this machine's host link allows the streaming path at this N
+    for i in range(2):
+        eng.host_copy_probe_async(host_in, outs[i & 1])
+    eng.host_sync()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        eng.host_copy_probe_async(host_in, outs[i & 1])
+    eng.host_sync()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    copy_ceiling = out_pix_per_step * args.steps / float(t.item()) / 1e6
 
     # ---------------- the same step on natural-like frames (reported beside the headline) ----------------
     natural = None
@@ -388,12 +487,27 @@ def main():
             eng.infer_device(d_nat, d_out)
         n1.record()
         torch.cuda.synchronize()
-        natural = {"value": F * H * W * SCALE * SCALE * 10 / (n0.elapsed_time(n1) * 1e-3) / 1e6, "unit": "Mpix/s",
+        natural = {"value": F * HL * W * SCALE * SCALE * 10 / (n0.elapsed_time(n1) * 1e-3) / 1e6, "unit": "Mpix/s",
                    "steps": 10, "frames": "mirror-tiled crops of the reference's golden Set5 results, device-resident"}
         del d_nat
 
+    # ---------------- cfg4: the LUT finetune step (every rank takes part: data-parallel, one all-reduce per step) ----------------
+    finetune = None
+    if not args.no_finetune:
+        del d_in, d_out
+        torch.cuda.empty_cache()
+        from tools.finetune_bench import finetune_block
+        try:
+            finetune, ft_state = finetune_block(rank, world, local, dist if world > 1 else None, steps=args.finetune_steps,
+                                                warmup=10, clock_sampler=lambda: ClockSampler(local))
+            del ft_state                       # the captured graphs hold NCCL work: dropped before the group goes away
+        except Exception as e:
+            finetune = {"error": repr(e)[:400]}
+        torch.cuda.synchronize()
+
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -413,28 +527,13 @@ def main():
         "bin_hist":      (0, 0, 2, None, "K1f preparation: streaming"),
         "bin_orphans":   (0, 0, 0, None, "K1f orphan list"),
     }
-    samples_per_step = F * H * W * C
+    samples_per_step = F * HL * W * C
     hbm_peak, peak_src = measured_peaks()
     dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, (0.0, 0))
     dom_name, (dom_ms, dom_n) = dom
     n_gather, b_gather, hbm_b, peak_variant, kdesc = KINFO.get(dom_name, (0, 0, HBM_B, None, ""))
     per_launch_s = dom_ms * 1e-3 / max(dom_n, 1)
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(tp):
-        try:
-            t = json.load(open(tp)).get(dom_name)
-            if t is not None:      # measured DRAM bytes per input sample (ncu --set full), scaled to this launch
-                traffic = t["dram_bytes_per_sample"] * samples_per_step
-        except Exception:
-            traffic = None
-    ach_hbm = samples_per_step * hbm_b / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": ach_hbm, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach_hbm / hbm_peak, "traffic": traffic, "peak_source": peak_src + " (burst copy figure)",
-                "alg_bytes_per_sample": hbm_b, "launch_ms": per_launch_s * 1e3,
-                "share_of_step": dom_ms / ms if ms > 0 else None,
-                "note": "the path is gather/ALU bound on chip, not HBM bound (5 B of HBM per 300 B gathered): "
-                        "see gather_roofline"}
+    step_s = ms * 1e-3 / args.steps
     gp = gather_peak(local)
 
     def peak_gathers(variant):
@@ -443,75 +542,124 @@ def main():
             return None
         return g * 5 if variant.startswith("quad_cell") else g   # one cell fetch serves the 5 vertices of an interpolation
 
+    # measured DRAM bytes per input sample and kernel (one ncu --set full capture per kernel, profiles/traffic.json)
+    traffic_tab = {}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tp):
+        try:
+            traffic_tab = {k: v for k, v in json.load(open(tp)).items() if isinstance(v, dict)}
+        except Exception:
+            traffic_tab = {}
+
+    # PRIMARY roofline: the path is bound by ON-CHIP gathers (300 B of LUT rows per input sample against 5 B of
+    # HBM), so the dominant kernel's algorithmic vertex-row bytes per second are set against the measured rate
+    # of the same gather primitive (ONE fixed peak per primitive: best launch shape of mulut_gather_bench).
     ach_gathers = samples_per_step * n_gather / per_launch_s if per_launch_s > 0 else 0.0
     pk = peak_gathers(peak_variant) if peak_variant else None
-    per_kernel = {}
+    per_kernel, t_peak_sum = {}, 0.0
     for kname, (kms, kn) in prof.items():
-        ng, bg, _, pv, _ = KINFO.get(kname, (0, 0, 0, None, ""))
-        if not ng or not kn:
+        ng, bg, kh, pv, _ = KINFO.get(kname, (0, 0, 0, None, ""))
+        if not kn:
             continue
-        g = samples_per_step * ng / (kms * 1e-3 / kn)
-        kp = peak_gathers(pv)
-        per_kernel[kname] = {"Ggathers_per_s": g / 1e9, "GBps": g * bg / 1e9, "peak_primitive": pv,
-                             "frac": g / kp if kp else None}
-    gather_roofline = {
-        "bound": "on-chip gather (shared memory / L1-L2)", "kernel": dom_name, "kernel_desc": kdesc,
-        "achieved": ach_gathers * b_gather / 1e9, "unit": "GB/s",
-        "achieved_Ggathers_per_s": ach_gathers / 1e9,
-        "alg_gathers_per_sample": n_gather, "alg_bytes_per_gather": b_gather,
-        "peak": pk * b_gather / 1e9 if pk else None,
-        "peak_Ggathers_per_s": pk / 1e9 if pk else None,
-        "peak_def": "micro-benchmark '{}' measured live (mulut_gather_bench): independent random gathers of the same "
-                    "shape from a table of the same kind, all SMs".format(peak_variant),
+        k_s = kms * 1e-3 / kn
+        if ng:
+            g = samples_per_step * ng / k_s
+            kp = peak_gathers(pv)
+            per_kernel[kname] = {"Ggathers_per_s": g / 1e9, "GBps": g * bg / 1e9, "peak_primitive": pv,
+                                 "frac": g / kp if kp else None, "launch_ms": k_s * 1e3}
+            if kp:
+                t_peak_sum += samples_per_step * ng / kp
+        elif kh:                               # streaming kernels: their floor is the HBM time of their algorithmic bytes
+            t_peak_sum += samples_per_step * kh / (hbm_peak * 1e9)
+    dom_traffic = traffic_tab.get(dom_name, {}).get("dram_bytes_per_sample")
+    roofline = {
+        "bound": "on-chip gather (shared memory / L1-L2): not hbm, not tensor - see roofline_hbm for the HBM side",
+        "kernel": dom_name, "kernel_desc": kdesc,
+        "achieved": ach_gathers * b_gather / 1e9, "peak": pk * b_gather / 1e9 if pk else None, "unit": "GB/s",
         "frac": ach_gathers / pk if pk else None,
-        "whole_step_Ggathers_per_s": samples_per_step * 120 * args.steps / (ms * 1e-3) / 1e9 if STAGES == 2 else None,
-        # the north star's own yardstick: the L2 gather roofline.  The shared-memory kernels are not bound by it -
-        # the whole step delivers more vertex rows per second than L2 can serve with its best fetch shape
-        # (one 64-byte cell = the 5 vertices of an interpolation) or with plain 4-byte gathers.
+        "traffic": dom_traffic * samples_per_step if dom_traffic is not None else None,
+        "traffic_def": "DRAM bytes of this kernel per launch (ncu dram__bytes_read+write per sample from profiles/traffic.json "
+                       "x samples per launch); its algorithmic HBM bytes are {} B/sample".format(hbm_b),
+        "achieved_Ggathers_per_s": ach_gathers / 1e9, "peak_Ggathers_per_s": pk / 1e9 if pk else None,
+        "alg_gathers_per_sample": n_gather, "alg_bytes_per_gather": b_gather,
+        "peak_def": "mulut_gather_bench '{}' measured live: independent random gathers of this shape from the same memory "
+                    "level on all SMs, best launch shape ({})".format(peak_variant, gp.get(peak_variant, {})),
+        "launch_ms": per_launch_s * 1e3, "share_of_step": dom_ms / ms if ms > 0 else None,
+        "whole_step": {"frac": t_peak_sum / step_s if step_s > 0 else None,
+                       "def": "sum over the step's kernels of (algorithmic gathers / primitive peak, or algorithmic HBM bytes / "
+                              "HBM peak for the streaming kernels) divided by the measured step time",
+                       "Ggathers_per_s": samples_per_step * 60 * STAGES / step_s / 1e9},
+        "per_kernel": per_kernel,
+        # the north star's own yardstick: the L2 gather roofline.  The shared-memory kernels are not bound by it - the
+        # whole step delivers more vertex rows per second than L2 serves with its best fetch shape
         "whole_step_vs_l2_gather_roofline": {
             "l2_cell64_x5_Ggathers_per_s": (peak_gathers("quad_cell64") or 0) / 1e9,
             "l2_u32_Ggathers_per_s": (peak_gathers("ldg_u32") or 0) / 1e9,
-            "frac_of_l2_cell64": (samples_per_step * 60 * STAGES * args.steps / (ms * 1e-3)) / peak_gathers("quad_cell64")
+            "frac_of_l2_cell64": (samples_per_step * 60 * STAGES / step_s) / peak_gathers("quad_cell64")
             if peak_gathers("quad_cell64") else None,
-            "frac_of_l2_u32": (samples_per_step * 60 * STAGES * args.steps / (ms * 1e-3)) / peak_gathers("ldg_u32")
+            "frac_of_l2_u32": (samples_per_step * 60 * STAGES / step_s) / peak_gathers("ldg_u32")
             if peak_gathers("ldg_u32") else None,
         },
-        "per_kernel": per_kernel,
         "microbench": gp,
     }
+    # HBM side, WHOLE step: algorithmic = 1 B read + r^2 B written per input sample
+    step_traffic = None
+    if traffic_tab and prof and all(k in traffic_tab for k in prof):
+        step_traffic = sum(traffic_tab[k]["dram_bytes_per_sample"] for k in prof) * samples_per_step
+    ach_hbm = samples_per_step * HBM_B / step_s / 1e9 if step_s > 0 else 0.0
+    roofline_hbm = {"bound": "hbm", "scope": "whole step", "achieved": ach_hbm, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach_hbm / hbm_peak, "alg_bytes_per_sample": HBM_B,
+                    "traffic": step_traffic,
+                    "traffic_bytes_per_sample": step_traffic / samples_per_step if step_traffic else None,
+                    "traffic_GBps": step_traffic / step_s / 1e9 if step_traffic else None,
+                    "peak_source": peak_src + " (burst copy figure)",
+                    "note": "structurally small: 5 B of HBM per 300 B gathered on chip"}
     kernels = {k: {"ms_total": v[0], "launches": v[1], "ms_per_launch": v[0] / v[1]} for k, v in prof.items()}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         v, cores, n, dt_cpu = cpu_port_throughput(args.cpu_seconds, 64)
         cpu = {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port",
-               "sample": "{} frame(s) 1920x1080 in {:.1f} s, C port of the reference algorithm (oracle/mulut_oracle.c), "
-                         "pthreads over rows".format(n, dt_cpu)}
+               "sample": "{} frame(s) {}x{} in {:.1f} s, C port of the reference algorithm (oracle/mulut_oracle.c), "
+                         "pthreads over rows".format(n, W, H, dt_cpu)}
+        if not args.no_numpy_ref:
+            try:
+                cpu["numpy_ref"] = numpy_reference_throughput(args.config)
+            except Exception as e:
+                cpu["numpy_ref"] = {"error": repr(e)[:300]}
 
     line = {
         "metric": "output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "strong" if strip else "weak",
         "vs_baseline": None, "dtype": "u8",
         "data": "synthetic" if DATA == "uniform" else "synthetic (mirror-tiled natural crops)",
         "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "kernel": args.kernel,
                    "l2": "per-step working set per GPU = {:.0f} MB in + {:.0f} MB out (> 126 MB L2), no flush".format(
-                       F * H * W * C / 1e6, F * H * W * C * SCALE * SCALE / 1e6),
-                   "parallelism": "frames sharded over {} GPU(s), no collective".format(world)},
-        "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": F * H * W * C,
-                "d2h_bytes_per_step": F * H * W * C * SCALE * SCALE, "api": "LutEngine.infer_host_async x steps + host_sync -> mulut_sr_infer_u8_host_async / mulut_sr_host_sync",
+                       F * HL * W * C / 1e6, F * HL * W * C * SCALE * SCALE / 1e6),
+                   "parallelism": ("every frame strip-sharded over {} GPUs ({} + {} halo rows on rank 0), no collective".format(
+                       world, row_e - row_b, HL - (row_e - row_b)) if strip else
+                       "frames sharded over {} GPU(s), no collective".format(world))},
+        "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": F * HL * W * C,
+                "d2h_bytes_per_step": F * HL * W * C * SCALE * SCALE, "api": "LutEngine.infer_host_async x steps + host_sync -> mulut_sr_infer_u8_host_async / mulut_sr_host_sync",
                 "sync_per_step": {"value": e2e_sync_value, "unit": "Mpix/s", "api": "LutEngine.infer_host -> mulut_sr_infer_u8_host, one blocking call per step"},
+                "copy_ceiling": {"value": copy_ceiling, "unit": "Mpix/s", "frac": e2e_value / copy_ceiling if copy_ceiling > 0 else None,
+                                 "def": "the same per-frame H2D + D2H copies on the same lanes with no kernels (mulut_host_copy_probe_async), "
+                                        "all {} rank(s) at once: the host-link ceiling of this machine at this N".format(world)},
                 "host_memory": "pinned", "check": sanity},
         "gpu_launches": int(launches) * world,
         "parity": parity,
         "clocks": clocks,
         "roofline": roofline,
-        "gather_roofline": gather_roofline,
+        "roofline_hbm": roofline_hbm,
         "kernels": kernels,
         "natural_frames": natural,
         "cpu_baseline": cpu,
+        "finetune": finetune,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

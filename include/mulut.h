@@ -55,8 +55,9 @@ const char *mulut_last_error(void);
 /*
  * Replaces the LUT loading block of sr/4_test_lut.py:323-333 (the caller still
  * reads the .npy files with the reference's naming rule).  Uploads the tables
- * to `device`, builds the device-side re-layouts and pins them in L2
- * (cudaAccessPolicyWindow on the streams used by *_host).
+ * to `device` and builds the device-side re-layouts.  With MULUT_L2_PERSIST=1 in the environment the
+ * tables are also pinned in L2 (cudaAccessPolicyWindow on the streams used by *_host; this raises the
+ * device-global persisting-L2 limit until the handle is destroyed - off by default, measured unnecessary).
  *   modes      NUL-terminated string over {s,d,y}, e.g. "sdy"  (--modes)
  *   host_luts  stage-major, mode-minor: host_luts[s*strlen(modes)+m]
  *   lut_rows   rows of every table (must be >= L^4), normally 83521
@@ -74,7 +75,9 @@ int mulut_reserve(mulut_handle_t handle, int N, int H, int W, int C);
  * (stages x modes x 4 rotations of FourSimplexInterpFaster + epilogue).
  *   d_in   uint8 (N, H, W, C) interleaved (PIL / HWC order)
  *   d_out  uint8 (N, H*scale, W*scale, C)
- * Bit-exact with the reference's numpy path.
+ * Bit-exact with the reference's numpy path.  Asynchronous on `stream`.  One handle serves up to 8
+ * distinct streams concurrently (each gets its own intermediates); the host side of a call is
+ * serialised per handle.
  */
 int mulut_sr_infer_u8(mulut_handle_t handle, const uint8_t *d_in, uint8_t *d_out,
                       int N, int H, int W, int C, void *stream);
@@ -93,6 +96,12 @@ int mulut_sr_infer_u8_host(mulut_handle_t handle, const uint8_t *h_in, uint8_t *
 int mulut_sr_infer_u8_host_async(mulut_handle_t handle, const uint8_t *h_in, uint8_t *h_out,
                                  int N, int H, int W, int C);
 int mulut_sr_host_sync(mulut_handle_t handle);
+
+/* The copies of mulut_sr_infer_u8_host_async with NO kernels between them (same lanes, same per-frame
+ * cudaMemcpyAsync calls, same bytes): the host-link ceiling of the streaming path on this machine.
+ * Diagnostic entry for bench.py's e2e.copy_ceiling; h_out receives stale device bytes. */
+int mulut_host_copy_probe_async(mulut_handle_t handle, const uint8_t *h_in, uint8_t *h_out,
+                                int N, int H, int W, int C);
 
 /* number of kernel launches issued by this handle since creation */
 long long mulut_launch_count(mulut_handle_t handle);

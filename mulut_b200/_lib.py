@@ -40,6 +40,8 @@ SYMBOLS = {
                                           _c.c_int]),
     "mulut_sr_infer_u8_host_async": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
                                           _c.c_int]),
+    "mulut_host_copy_probe_async": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
+                                          _c.c_int]),
     "mulut_sr_host_sync": (_c.c_int, [_c.c_void_p]),
     "mulut_launch_count": (_c.c_longlong, [_c.c_void_p]),
     "mulut_profile_enable": (_c.c_int, [_c.c_void_p, _c.c_int]),

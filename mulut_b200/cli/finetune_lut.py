@@ -6,7 +6,12 @@ Adam(lr0, betas .9/.999, eps 1e-8) with the cosine LambdaLR lr0 -> lr1
 runs in the sm_100a kernels; multi-GPU is real data parallelism (one NCCL
 all-reduce of the flat 17 MB LUT-gradient buffer per step) instead of the
 reference's non-functional `--gpuNum` branch (:156-157); `--synthetic` trains on
-seeded random patches because the DIV2K set is not shipped.
+seeded random patches because the DIV2K set is not shipped (any iterator of (im, lb) batches can be
+passed to `finetune_steps(batches=...)`); `--displayStep` prints the running loss (:142-149),
+`--valStep` runs `valid_steps` (:23-65, whole-image C=3 inference through the torch path) when the
+benchmark folders exist under `--valDir`, and `--saveStep` additionally exports the LUTs and the
+optimiser state every N steps so a long run can resume with `--startIter` (the reference saves once,
+at the end).
 """
 from __future__ import annotations
 
@@ -39,6 +44,60 @@ def synthetic_batch(batch: int, crop: int, scale: int, seed: int, device):
     im = torch.randint(0, 256, (batch, 1, crop, crop), generator=g).float() / 255.0
     lb = torch.randint(0, 256, (batch, 1, crop * scale, crop * scale), generator=g).float() / 255.0
     return im.to(device), lb.to(device)
+
+
+def load_benchmarks(val_dir: str, scale: int, datasets=("Set5", "Set14", "B100", "Urban100", "Manga109")):
+    """{dataset: [(name, lr uint8 HWC, hr uint8 HWC)]} for the benchmark folders that exist under `val_dir`
+    (layout of sr/data.py:127-168: <dataset>/HR/*.png and <dataset>/LR_bicubic/X<scale>/*.png)."""
+    import os
+    from PIL import Image
+    from ..metrics import modcrop
+    out = {}
+    for ds in datasets:
+        folder = os.path.join(val_dir, ds, "HR")
+        if not os.path.isdir(folder):
+            continue
+        items = []
+        for f in sorted(os.listdir(folder)):
+            hr = modcrop(np.array(Image.open(os.path.join(folder, f))), scale)
+            lr = np.array(Image.open(os.path.join(val_dir, ds, "LR_bicubic/X%d" % scale, f)))
+            if hr.ndim == 2:
+                hr = np.stack([hr] * 3, axis=2)
+            if lr.ndim == 2:
+                lr = np.stack([lr] * 3, axis=2)
+            items.append((f[:-4], np.ascontiguousarray(lr[:, :, :3]), np.ascontiguousarray(hr[:, :, :3])))
+        out[ds] = items
+    return out
+
+
+def valid_steps(model_G, benchmarks, scale: int, it: int, out_dir=None, log=print):
+    """sr/3_finetune_lut.py:23-65: whole images ([1,3,H,W], any non-square size) through MuLUT.forward,
+    round(clip(pred*255)) -> uint8, PSNR / SSIM on the BT.601 luma (on the device:
+    mulut_eval_psnr_ssim_y_u8).  Returns {dataset: (mean PSNR, mean SSIM)}."""
+    import os
+    from ..metrics import psnr_ssim_device
+    device = next(model_G.parameters()).device
+    res = {}
+    was_training = model_G.training
+    with torch.no_grad():
+        model_G.eval()
+        for ds, items in benchmarks.items():
+            psnrs, ssims = [], []
+            for name, lr, hr in items:
+                im = torch.from_numpy(lr.astype(np.float32) / 255.0).permute(2, 0, 1)[None].to(device)
+                pred = model_G(im) * 255.0
+                pred = torch.round(torch.clamp(pred[0].permute(1, 2, 0), 0, 255)).to(torch.uint8).contiguous()
+                p, s = psnr_ssim_device(pred, torch.from_numpy(hr).to(device), scale)
+                psnrs.append(p)
+                ssims.append(s)
+                if out_dir is not None:
+                    from PIL import Image
+                    os.makedirs(os.path.join(out_dir, ds), exist_ok=True)
+                    Image.fromarray(pred.cpu().numpy()).save(os.path.join(out_dir, ds, "{}_lutft.png".format(name)))
+            res[ds] = (float(np.mean(psnrs)), float(np.mean(ssims)))
+            log("Iter {} | Dataset {} | AVG PSNR: {:02f}, AVG: SSIM: {:04f}".format(it, ds, res[ds][0], res[ds][1]))
+    model_G.train(was_training)
+    return res
 
 
 class GraphedStep:
@@ -90,36 +149,66 @@ class GraphedStep:
 
 
 def finetune_steps(model_G: MuLUT, steps: int, batch: int, crop: int, seed: int, lr0: float, lr1: float,
-                   total_iter: int, weight_decay: float = 0.0, batches=None, graph: bool = False):
+                   total_iter: int, weight_decay: float = 0.0, batches=None, graph: bool = False,
+                   start_iter: int = 0, display_step: int = 0, on_step=None, log=print, state=None):
     """The training loop body of 3_finetune_lut.py:118-136 on this rank's share.
-    graph=True replays the step as one CUDA graph (same arithmetic; needs a fixed batch shape)."""
-    if graph:
-        rank, world, _ = mdist.env_rank_world()
-        device = next(model_G.parameters()).device
-        r = model_G.upscale
-        C = 1 if batches is None else batches[0][0].shape[1]
-        b0 = batch if batches is None else batches[0][0].shape[0]
-        model_G.train()
-        gs = GraphedStep(model_G, (b0, C, crop, crop), (b0, C, crop * r, crop * r), lr0, weight_decay)
-        lam = lr_lambda(total_iter, lr0, lr1)
-        losses = []
-        for i in range(steps):
-            im, lb = batches[i] if batches is not None else synthetic_batch(batch, crop, r, seed + i * world + rank, device)
-            losses.append(gs(im, lb, lr0 * lam(i)))     # LambdaLR: lr of step i is lr0 * lambda(i)
-        return [float(l) for l in torch.stack(losses).cpu()] if losses else []
+    graph=True replays the step as one CUDA graph (same arithmetic; needs a fixed batch shape).
+    batches: None (seeded synthetic patches) or any iterable of (im, lb) CUDA batches - a list, a generator,
+    a DataLoader wrapper.  display_step: every N steps the mean loss of the last N is synchronised, logged
+    and the stored device scalars are dropped.  on_step(i, optimiser): called after step i (1-based, like
+    the reference's loop) - the CLI hangs validation and checkpoints on it.  state: optimiser state to resume
+    from (see `checkpoint`).  Returns the per-step losses as floats."""
     rank, world, _ = mdist.env_rank_world()
     device = next(model_G.parameters()).device
+    r = model_G.upscale
+    it = iter(batches) if batches is not None else None
+    first = next(it) if it is not None else None
+    lam = lr_lambda(total_iter, lr0, lr1)
+    model_G.train()
+    losses, pending = [], []
+
+    def flush(i):
+        if pending:
+            vals = [float(v) for v in torch.stack(pending).cpu()]
+            losses.extend(vals)
+            pending.clear()
+            if display_step and rank == 0:
+                log("Iter:{:6d}, loss:{:.3e}".format(i, float(np.mean(vals))))
+
+    def batch_of(i):
+        nonlocal first
+        if it is None:
+            return synthetic_batch(batch, crop, r, seed + i * world + rank, device)
+        if first is not None:
+            b, first = first, None
+            return b
+        return next(it)
+
+    if graph:
+        C = 1 if first is None else first[0].shape[1]
+        b0 = batch if first is None else first[0].shape[0]
+        hw = (crop, crop) if first is None else tuple(first[0].shape[2:])
+        gs = GraphedStep(model_G, (b0, C) + hw, (b0, C, hw[0] * r, hw[1] * r), lr0, weight_decay)
+        if state is not None:
+            gs.opt.load_state(state)
+        for k in range(steps):
+            i = start_iter + k
+            im, lb = batch_of(i)
+            pending.append(gs(im, lb, lr0 * lam(i)))       # LambdaLR: lr of step i is lr0 * lambda(i)
+            if display_step and (i + 1) % display_step == 0:
+                flush(i + 1)
+            if on_step is not None:
+                on_step(i + 1, gs.opt)
+        flush(start_iter + steps)
+        del gs                                              # the captured graph (it holds NCCL work) goes before the group
+        return losses
     params = [p for p in model_G.parameters() if p.requires_grad]
     bucket = mdist.FlatGradBucket(params)
     opt_G = torch.optim.Adam(params, lr=lr0, betas=(0.9, 0.999), eps=1e-8, weight_decay=weight_decay)
-    sched = torch.optim.lr_scheduler.LambdaLR(opt_G, lr_lambda=lr_lambda(total_iter, lr0, lr1))
-    losses = []
-    model_G.train()
-    for i in range(steps):
-        if batches is not None:
-            im, lb = batches[i]
-        else:
-            im, lb = synthetic_batch(batch, crop, model_G.upscale, seed + i * world + rank, device)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt_G, lr_lambda=lambda x: lam(x + start_iter))
+    for k in range(steps):
+        i = start_iter + k
+        im, lb = batch_of(i)
         bucket.zero_()
         pred = model_G(im)
         loss = F.mse_loss(pred, lb)
@@ -127,11 +216,27 @@ def finetune_steps(model_G: MuLUT, steps: int, batch: int, crop: int, seed: int,
         bucket.all_reduce_mean()
         opt_G.step()
         sched.step()
-        losses.append(float(loss.item()))
+        pending.append(loss.detach())
+        if display_step and (i + 1) % display_step == 0:
+            flush(i + 1)
+        if on_step is not None:
+            on_step(i + 1, None)
+    flush(start_iter + steps)
     return losses
 
 
+def checkpoint(model_G: MuLUT, opt, exp_dir: str, it: int) -> None:
+    """LUT export (the reference's .npy format) + parameters and Adam moments for --startIter."""
+    import os
+    model_G.export_luts(exp_dir)
+    blob = {"iter": it, "params": {n: p.detach().cpu() for n, p in model_G.named_parameters()}}
+    if opt is not None:
+        blob["adam"] = opt.state()
+    torch.save(blob, os.path.join(exp_dir, "Finetune_{:06d}.pth".format(it)))
+
+
 def main(argv=None):
+    import os
     opt = TrainOptions().parse(argv)
     rank, world, local = mdist.init_process_group()
     device = torch.device("cuda", local if world > 1 else opt.device)
@@ -142,23 +247,40 @@ def main(argv=None):
     if not opt.synthetic:
         raise SystemExit("only --synthetic training data is available in this build "
                          "(DIV2K is not shipped; see DESIGN.md, out of scope: data providers)")
+    state = None
+    if opt.startIter > 0:                     # resume: parameters + Adam moments written by --saveStep
+        blob = torch.load(os.path.join(opt.expDir, "Finetune_{:06d}.pth".format(opt.startIter)), map_location=device)
+        with torch.no_grad():
+            for n, p in model_G.named_parameters():
+                p.copy_(blob["params"][n])
+        state = blob.get("adam")
+    benchmarks = load_benchmarks(opt.valDir, opt.scale) if (rank == 0 and opt.valStep > 0 and os.path.isdir(opt.valDir)) else {}
+
+    def on_step(i, optimiser):
+        if rank != 0:
+            return
+        if benchmarks and (i % opt.valStep == 0 or i == 1):           # 3_finetune_lut.py:152-157
+            valid_steps(model_G, benchmarks, opt.scale, i, os.path.join(opt.expDir, "val"))
+        if opt.saveStep > 0 and i % opt.saveStep == 0:
+            checkpoint(model_G, optimiser, opt.expDir, i)
+
     per_rank = max(1, opt.batchSize // world)
     st = time.time()
-    losses = finetune_steps(model_G, opt.totalIter, per_rank, opt.cropSize, 0, opt.lr0, opt.lr1, opt.totalIter,
-                            opt.weightDecay, graph=not getattr(opt, "eager", False))
+    n_steps = max(0, opt.totalIter - opt.startIter)
+    losses = finetune_steps(model_G, n_steps, per_rank, opt.cropSize, 0, opt.lr0, opt.lr1, opt.totalIter,
+                            opt.weightDecay, graph=not getattr(opt, "eager", False), start_iter=opt.startIter,
+                            display_step=opt.displayStep, on_step=on_step, state=state)
     if rank == 0:
-        print("{} | Iter:{:6d}, loss:{:.3e}, rT:{:.4f}".format(opt.expDir, opt.totalIter, np.mean(losses[-100:]),
-                                                          (time.time() - st) / max(1, opt.totalIter)))
+        print("{} | Iter:{:6d}, loss:{:.3e}, rT:{:.4f}".format(opt.expDir, opt.totalIter, np.mean(losses[-100:]) if losses else float("nan"),
+                                                          (time.time() - st) / max(1, n_steps)))
         model_G.export_luts(opt.expDir)
         print("Finetuned LUT saved to {}".format(opt.expDir))
     if world > 1:
-        # communicators captured in a CUDA graph can hang in their destructor: leave without tearing them down
-        import os
+        # the step graph (which captured the all-reduce) was destroyed inside finetune_steps: the group can go
         torch.cuda.synchronize()
         torch.distributed.barrier()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        torch.distributed.destroy_process_group()
+    return losses
 
 
 if __name__ == "__main__":

@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "binned.cuh"
 #include "common.cuh"
 #include "infer.cuh"
@@ -27,6 +29,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 }
 
 constexpr int HOST_LANES = 3;      // frames in flight on the host path
+constexpr int MAX_DEV_STREAMS = 8; // distinct caller streams one handle serves concurrently (device API)
 
 struct Workspace {
     uint8_t *img[2] = {nullptr, nullptr};   // stage intermediates (ping-pong)
@@ -54,7 +57,15 @@ struct mulut_handle_s {
     const uint8_t *lut_alt[MULUT_MAX_STAGES][MULUT_MAX_MODES] = {};
     const uint8_t *lut_slab[MULUT_MAX_MODES] = {};   // last stage, up = 2 only
     TapTable taps;
-    Workspace ws[1 + HOST_LANES];           // [0] device API, [1..] host-path lanes
+    Workspace ws[HOST_LANES];               // host-path lanes
+    // device API: one workspace per caller stream, so calls on different streams never share intermediates
+    // ("concurrent calls on different streams allowed").  Slot 0 is what mulut_reserve sizes; the
+    // first stream to call adopts it.
+    Workspace dev_ws[MAX_DEV_STREAMS];
+    cudaStream_t dev_stream[MAX_DEV_STREAMS] = {};
+    bool dev_used[MAX_DEV_STREAMS] = {};
+    std::mutex mu;                          // serialises the HOST side of every call on this handle (enqueue only)
+    bool l2_limit_set = false;
     cudaStream_t lane_stream[HOST_LANES] = {};
     uint8_t *lane_in[HOST_LANES] = {}, *lane_out[HOST_LANES] = {};
     size_t lane_in_bytes = 0, lane_out_bytes = 0;
@@ -324,8 +335,11 @@ int mulut_create(mulut_handle_t *handle, int device, int stages, const char *mod
 
     // L2 residency: keep the LUT allocation in the persisting carve-out for the
     // library's own streams (the tables are 1.3-14 MB; L2 is 126 MB).
+    // Opt-in (MULUT_L2_PERSIST=1): the carve-out is a DEVICE-GLOBAL limit shared with every other user of the
+    // context, and it measured unnecessary - without it K1e's LUT reads hit L2 at 98 % (the tables are 1.3-50 MB
+    // of a 126 MB L2 and the frames stream through once); see DESIGN.md section 4.
     const char *env = getenv("MULUT_L2_PERSIST");
-    const bool persist = !(env && env[0] == '0');
+    const bool persist = env && env[0] == '1';
     for (int i = 0; i < HOST_LANES; ++i) {
         e = cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking);
         if (e != cudaSuccess) { mulut_destroy(h); return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
@@ -333,7 +347,10 @@ int mulut_create(mulut_handle_t *handle, int device, int stages, const char *mod
     if (persist && prop.persistingL2CacheMaxSize > 0) {
         size_t want = h->lut_bytes < (size_t)prop.persistingL2CacheMaxSize ? h->lut_bytes
                                                                            : (size_t)prop.persistingL2CacheMaxSize;
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+        size_t cur = 0;
+        cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+        if (cur >= want || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            h->l2_limit_set = cur < want;
             cudaStreamAttrValue attr;
             memset(&attr, 0, sizeof attr);
             attr.accessPolicyWindow.base_ptr = h->d_luts;
@@ -362,6 +379,11 @@ int mulut_destroy(mulut_handle_t h)
         cudaFree(h->lane_out[i]);
     }
     for (auto &w : h->ws) ws_free(w);
+    for (auto &w : h->dev_ws) ws_free(w);
+    if (h->l2_limit_set) {                  // MULUT_L2_PERSIST=1 raised the device-global carve-out: give it back
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    }
     for (int i = 0; i < h->prof.n_events; ++i) { cudaEventDestroy(h->prof.recs[i].e0); cudaEventDestroy(h->prof.recs[i].e1); }
     cudaFree(h->d_luts);
     delete h;
@@ -425,17 +447,27 @@ int mulut_reserve(mulut_handle_t h, int N, int H, int W, int C)
     int rc = check_shape(h, (void *)1, (void *)1, N, H, W, C);
     if (rc) return rc;
     MULUT_CUDA(cudaSetDevice(h->device));
-    rc = ws_reserve(h->ws[0], h->stages, h->n_modes, (size_t)N * H * W * C, h->interval == 4,
-                    h->scale == 2 && h->interval == 4);
-    if (rc) return rc;
-    // the pitched staging copy of frames TMA cannot map in place (sized for the worst case: the caller's
-    // pointer may turn out to be misaligned even when W*C is a multiple of 16)
-    Workspace &w = h->ws[0];
-    const size_t need = (size_t)N * H * (((size_t)W * C + 15) / 16 * 16);
-    if (h->interval == 4 && C <= 4 && w.pitched_bytes < need) {
-        cudaFree(w.pitched); w.pitched = nullptr; w.pitched_bytes = 0;
-        MULUT_CUDA(cudaMalloc(&w.pitched, need));
-        w.pitched_bytes = need;
+    std::lock_guard<std::mutex> lock(h->mu);
+    // every workspace a stream already uses, plus the next unclaimed one (the one a new stream - e.g. the
+    // stream of a CUDA-graph capture - will adopt): after this call the hot path allocates nothing
+    bool spare_done = false;
+    for (int i = 0; i < MAX_DEV_STREAMS; ++i) {
+        if (!h->dev_used[i]) {
+            if (spare_done) continue;
+            spare_done = true;
+        }
+        Workspace &w = h->dev_ws[i];
+        rc = ws_reserve(w, h->stages, h->n_modes, (size_t)N * H * W * C, h->interval == 4,
+                        h->scale == 2 && h->interval == 4);
+        if (rc) return rc;
+        // the pitched staging copy of frames TMA cannot map in place (sized for the worst case: the caller's
+        // pointer may turn out to be misaligned even when W*C is a multiple of 16)
+        const size_t need = (size_t)N * H * (((size_t)W * C + 15) / 16 * 16);
+        if (h->interval == 4 && C <= 4 && w.pitched_bytes < need) {
+            cudaFree(w.pitched); w.pitched = nullptr; w.pitched_bytes = 0;
+            MULUT_CUDA(cudaMalloc(&w.pitched, need));
+            w.pitched_bytes = need;
+        }
     }
     return MULUT_OK;
 }
@@ -446,13 +478,29 @@ int mulut_sr_infer_u8(mulut_handle_t h, const uint8_t *d_in, uint8_t *d_out, int
     int rc = check_shape(h, d_in, d_out, N, H, W, C);
     if (rc) return rc;
     MULUT_CUDA(cudaSetDevice(h->device));
-    return run_stages(h, h->ws[0], d_in, d_out, N, H, W, C, (cudaStream_t)stream);
+    std::lock_guard<std::mutex> lock(h->mu);
+    // the workspace of this stream: the one it used before, else the first one no stream has claimed yet
+    // (slot 0 is the one mulut_reserve sized)
+    cudaStream_t st = (cudaStream_t)stream;
+    int slot = -1;
+    for (int i = 0; i < MAX_DEV_STREAMS && slot < 0; ++i)
+        if (h->dev_used[i] && h->dev_stream[i] == st) slot = i;
+    for (int i = 0; i < MAX_DEV_STREAMS && slot < 0; ++i)
+        if (!h->dev_used[i]) { h->dev_used[i] = true; h->dev_stream[i] = st; slot = i; }
+    if (slot < 0) {
+        set_error("mulut_sr_infer_u8: more than %d distinct streams on one handle (create another handle)", MAX_DEV_STREAMS);
+        return MULUT_E_BAD_ARG;
+    }
+    return run_stages(h, h->dev_ws[slot], d_in, d_out, N, H, W, C, st);
 }
 
-int mulut_sr_infer_u8_host_async(mulut_handle_t h, const uint8_t *h_in, uint8_t *h_out, int N, int H, int W, int C)
+// kernels = false: the same copies on the same lanes with no kernels between them - the host-link ceiling of
+// the streaming path (mulut_host_copy_probe_async; bench.py's e2e.copy_ceiling)
+static int host_async(mulut_handle_t h, const uint8_t *h_in, uint8_t *h_out, int N, int H, int W, int C, bool kernels)
 {
     int rc = check_shape(h, h_in, h_out, N, H, W, C);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lock(h->mu);
     const size_t fin = (size_t)H * W * C, fout = fin * h->scale * h->scale;
     if (N == 0 || fin == 0) return MULUT_OK;
     MULUT_CUDA(cudaSetDevice(h->device));
@@ -489,11 +537,23 @@ int mulut_sr_infer_u8_host_async(mulut_handle_t h, const uint8_t *h_in, uint8_t 
         const int cn = N - n < chunk ? N - n : chunk;
         cudaStream_t st = h->lane_stream[lane];
         MULUT_CUDA(cudaMemcpyAsync(h->lane_in[lane], h_in + (size_t)n * fin, fin * cn, cudaMemcpyHostToDevice, st));
-        rc = run_stages(h, h->ws[1 + lane], h->lane_in[lane], h->lane_out[lane], cn, H, W, C, st);
-        if (rc) return rc;
+        if (kernels) {
+            rc = run_stages(h, h->ws[lane], h->lane_in[lane], h->lane_out[lane], cn, H, W, C, st);
+            if (rc) return rc;
+        }
         MULUT_CUDA(cudaMemcpyAsync(h_out + (size_t)n * fout, h->lane_out[lane], fout * cn, cudaMemcpyDeviceToHost, st));
     }
     return MULUT_OK;
+}
+
+int mulut_sr_infer_u8_host_async(mulut_handle_t h, const uint8_t *h_in, uint8_t *h_out, int N, int H, int W, int C)
+{
+    return host_async(h, h_in, h_out, N, H, W, C, true);
+}
+
+int mulut_host_copy_probe_async(mulut_handle_t h, const uint8_t *h_in, uint8_t *h_out, int N, int H, int W, int C)
+{
+    return host_async(h, h_in, h_out, N, H, W, C, false);
 }
 
 int mulut_sr_host_sync(mulut_handle_t h)

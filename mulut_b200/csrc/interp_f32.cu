@@ -660,10 +660,24 @@ static int fill_args(F32Args &a, const float *weight, int n_rows, int up, char m
     return MULUT_OK;
 }
 
+static int sm_count()
+{
+    // multiProcessorCount of the current device (B200: 148), cached per device
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    }
+    return cached[dev];
+}
+
 static unsigned grid_for(size_t total)
 {
     size_t b = (total + 255) / 256;
-    if (b > 148 * 32) b = 148 * 32;
+    const size_t cap = (size_t)sm_count() * 32;
+    if (b > cap) b = cap;
     return (unsigned)(b ? b : 1);
 }
 
@@ -855,7 +869,7 @@ extern "C" int mulut_adam_step_f32(float *d_param, const float *d_grad, float *d
     cudaStream_t st = (cudaStream_t)stream;
     adam_tick_kernel<<<1, 1, 0, st>>>(d_step);
     size_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;
     adam_step_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, d_lr, beta1, beta2, eps,
                                                        weight_decay, d_step);
     MULUT_CUDA(cudaGetLastError());

@@ -126,5 +126,14 @@ class FusedAdam:
                 self.exp_avg_sq.data_ptr(), self.flat_param.numel(), self.lr.data_ptr(), self.betas[0], self.betas[1],
                 self.eps, self.weight_decay, self.step_count.data_ptr(), stream))
 
+    def state(self) -> dict:
+        """Moments, step counter and learning rate (host copies) - what a resumed run needs."""
+        return {"exp_avg": self.exp_avg.detach().cpu(), "exp_avg_sq": self.exp_avg_sq.detach().cpu(),
+                "step": float(self.step_count.item()), "lr": float(self.lr.item())}
+
+    def load_state(self, st: dict) -> None:
+        self.exp_avg.copy_(st["exp_avg"]); self.exp_avg_sq.copy_(st["exp_avg_sq"])
+        self.step_count.fill_(float(st["step"])); self.lr.fill_(float(st["lr"]))
+
     def reset_state(self) -> None:
         self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.step_count.zero_()

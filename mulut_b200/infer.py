@@ -188,6 +188,44 @@ class LutEngine:
         self._pending.append((frames, out))                      # keep the buffers alive until host_sync
         _lib.check(_lib.lib().mulut_sr_infer_u8_host_async(self._h, frames.ctypes.data, out.ctypes.data, N, H, W, C))
 
+    def host_copy_probe_async(self, frames: np.ndarray, out: np.ndarray) -> None:
+        """The H2D / D2H copies of :meth:`infer_host_async` with no kernels between them (bench.py's
+        e2e.copy_ceiling: what the host link of this machine allows the streaming path)."""
+        N, H, W, C = frames.shape
+        self._pending.append((frames, out))
+        _lib.check(_lib.lib().mulut_host_copy_probe_async(self._h, frames.ctypes.data, out.ctypes.data, N, H, W, C))
+
+    def infer_strip(self, frame, rank: int, world: int, out=None):
+        """Strip-sharded inference of ONE frame ("for single huge frames: horizontal strips with
+        a 4-row input halo"): computes rows [b*r, e*r) of the output, (b, e) = the `rank`-th of `world`
+        contiguous row ranges of the input, from input rows [b - halo, e + halo) with halo = 2 rows per
+        stage (each stage reads a 5x5 window).  No collective: concatenating the strips of all ranks along
+        the row axis gives the whole-frame bytes exactly - at the frame's own top/bottom edge the strip ends
+        at the edge, so the kernels' coordinate clamp supplies the reference's edge replication there, and
+        an interior strip's halo rows keep every kept output row out of reach of the strip's artificial edge.
+        frame: CUDA uint8 (H,W,C) tensor or host numpy array of that shape (only the strip's rows are read).
+        Returns (row_begin, row_end, strip) with strip of shape ((e-b)*r, W*r, C), same kind as `frame`."""
+        from .dist import shard_rows_with_halo
+        if frame.ndim != 3:
+            raise ValueError("infer_strip expects one (H,W,C) frame")
+        H = int(frame.shape[0])
+        r = self.scale
+        b, e, lb, le = shard_rows_with_halo(H, rank, world, 2 * self.stages)
+        if e <= b:
+            empty = frame[0:0]
+            return b, e, (empty.new_empty((0, frame.shape[1] * r, frame.shape[2])) if not isinstance(frame, np.ndarray)
+                          else np.empty((0, frame.shape[1] * r, frame.shape[2]), np.uint8))
+        piece = frame[lb:le]
+        if isinstance(frame, np.ndarray):
+            full = self.infer_host(np.ascontiguousarray(piece))
+        else:
+            full = self.infer_device(piece.contiguous())
+        strip = full[(b - lb) * r:(e - lb) * r]
+        if out is not None:
+            out[...] = strip
+            strip = out
+        return b, e, strip
+
     def host_sync(self) -> None:
         """Wait for every :meth:`infer_host_async` call issued so far."""
         try:

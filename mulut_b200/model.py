@@ -105,9 +105,19 @@ class _StageFunction(torch.autograd.Function):
         return (gx, None, None, None, None, None) + tuple(gws)
 
 
-def fused_stage(x, weights, upscale, modes, avg, bias, interval=4):
-    """x' = round(clamp(sum-with-per-pass-rounding / avg + bias, 0, 255)) for one stage."""
+def fused_stage(x, weights, upscale, modes, avg, bias, interval=4, check_inputs=False):
+    """x' = round(clamp(sum-with-per-pass-rounding / avg + bias, 0, 255)) for one stage.
+
+    PRECONDITION: `x` is integer-valued (0..255 as float32) - what MuLUT.forward feeds every stage
+    ((k/255)*255 is exact in fp32 and every stage output is rounded).  K4 splits the samples into MSB / LSB
+    with integer arithmetic; a fractional input would be truncated where the reference's float
+    floor_divide / % (model.py:123-131) keeps the fraction.  check_inputs=True validates this (one device
+    synchronisation; not inside a CUDA-graph capture); the un-fused path (MuLUT(fused=False), K2/K3) accepts
+    any float input."""
     modes = "".join(modes)
+    if check_inputs and not torch.cuda.is_current_stream_capturing():
+        if bool((x.detach() != torch.round(x.detach())).any()):
+            raise ValueError("fused_stage: the input is not integer-valued; use MuLUT(fused=False) for fractional inputs")
     for m in modes:
         if m not in ("s", "d", "y"):
             raise ValueError("Mode {} not implemented.".format(m))
@@ -123,11 +133,14 @@ def interp_torch_batch(weight, upscale, mode, img_in, bd, interval=4):
 class MuLUT(nn.Module):
     """PyTorch version of MuLUT for LUT-aware fine-tuning (kernel-backed)."""
 
-    def __init__(self, lut_folder, stages, modes, upscale=4, interval=4, luts=None, fused=True):
+    def __init__(self, lut_folder, stages, modes, upscale=4, interval=4, luts=None, fused=True, check_inputs=False):
         super().__init__()
         # fused=True: every stage is one K4 kernel per direction; fused=False keeps the reference's
-        # loop of 4*len(modes) InterpTorchBatch calls per stage (each a K2/K3 kernel) - same results
+        # loop of 4*len(modes) InterpTorchBatch calls per stage (each a K2/K3 kernel) - same results for the
+        # inputs the reference flow produces (x on the k/255 grid).  The fused kernels REQUIRE integer-valued
+        # stage inputs (see fused_stage); check_inputs=True verifies that on every call (debug: it synchronises)
         self.fused = fused
+        self.check_inputs = check_inputs
         self.interval = interval
         self.upscale = upscale
         self.modes = modes
@@ -170,7 +183,7 @@ class MuLUT(nn.Module):
                     if mode not in ("s", "d", "y"):
                         raise ValueError("Mode {} not implemented.".format(mode))
                 weights = [getattr(self, "weight_s{}_{}".format(stage, mode)) for mode in modes]
-                x = fused_stage(x, weights, scale, modes, avg_factor, bias, self.interval)
+                x = fused_stage(x, weights, scale, modes, avg_factor, bias, self.interval, self.check_inputs)
                 continue
             for mode in modes:
                 pad = mode_pad_dict[mode]

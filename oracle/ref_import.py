@@ -15,10 +15,21 @@ import sys
 import numpy as np
 
 REF_ROOT = os.environ.get("MULUT_REFERENCE_ROOT", "/root/reference")
+# the GPU box has no /root/reference: there the byte-identical staged copy made by `python -m oracle.fetch_ref`
+# (git-ignored, shipped with the snapshot) stands in for the modules of the hot path
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+if not os.path.isfile(os.path.join(REF_ROOT, "sr", "4_test_lut.py")) and \
+        os.path.isfile(os.path.join(_STAGED, "sr", "4_test_lut.py")):
+    REF_ROOT = _STAGED
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REF_ROOT, "sr", "4_test_lut.py"))
+
+
+def full_tree() -> bool:
+    """The whole reference repository (data, results, models), not just the staged hot-path modules."""
+    return os.path.isdir(os.path.join(REF_ROOT, "models", "sr_x2sdy"))
 
 
 _cache = {}

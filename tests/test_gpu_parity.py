@@ -225,6 +225,34 @@ def test_full_size_8k_x2_matches_c_oracle():
         hout = pinned_empty(ref.shape)
         eng.infer_host(frame, hout)
         assert (hout == ref).all()
+        del hout
+        # strip sharding of the single frame: 2 and 3 row strips with a 4-row halo, computed
+        # independently (as 2 / 3 GPUs would), concatenate to the whole-frame bytes
+        d = torch.from_numpy(frame[0]).cuda()
+        for world in (2, 3):
+            rows = []
+            for rank in range(world):
+                b, e, strip = eng.infer_strip(d, rank, world)
+                assert strip.shape == ((e - b) * 2, 15360, 3)
+                rows.append(strip.cpu().numpy())
+            assert (np.concatenate(rows, 0) == ref[0]).all(), world
+
+
+@pytest.mark.parametrize("scale,stages,H", [(2, 2, 37), (4, 2, 9), (2, 3, 23), (2, 1, 5), (3, 2, 2)])
+def test_strip_sharding_small_frames(scale, stages, H):
+    """infer_strip on frames where strips are thinner than the halo, world > rows, and host arrays."""
+    import torch
+    from mulut_b200.infer import LutEngine
+    rng = np.random.default_rng(H)
+    luts = O.random_luts(60 + H, stages, "sdy", scale)
+    img = rng.integers(0, 256, (H, 40, 3), dtype=np.uint8)
+    ref = CO.sr_u8(img, luts, stages, "sdy", scale)
+    with LutEngine(luts, stages, "sdy", scale, 4, device=0) as eng:
+        for world in (1, 2, 3, 8):
+            dev = [eng.infer_strip(torch.from_numpy(img).cuda(), r, world)[2].cpu().numpy() for r in range(world)]
+            assert (np.concatenate(dev, 0) == ref).all(), world
+            host = [eng.infer_strip(img, r, world)[2] for r in range(world)]
+            assert (np.concatenate(host, 0) == ref).all(), world
 
 
 def test_cfg1_batch_of_64_256x256_x4_matches_c_oracle(shipped_luts):
@@ -239,6 +267,37 @@ def test_cfg1_batch_of_64_256x256_x4_matches_c_oracle(shipped_luts):
         out = eng(torch.from_numpy(frames).cuda()).cpu().numpy()
         assert (out == ref).all(), int((out != ref).sum())
         assert (eng(frames) == ref).all()
+
+
+@pytest.mark.parametrize("kernel", [-1, 1])
+def test_one_handle_serves_concurrent_streams(kernel):
+    """concurrent calls on different streams of ONE handle (the LUTs are read-only; every stream
+    gets its own intermediates).  Different frames on three streams, interleaved without synchronising."""
+    import torch
+    from mulut_b200.infer import LutEngine
+    rng = np.random.default_rng(17)
+    luts = O.random_luts(18, 2, "sdy", 2)
+    frames = [rng.integers(0, 256, (2, 400, 480, 3), dtype=np.uint8) for _ in range(3)]
+    refs = [CO.sr_u8(f, luts, 2, "sdy", 2) for f in frames]
+    with LutEngine(luts, 2, "sdy", 2, 4, device=0, kernel=kernel) as eng:
+        streams = [torch.cuda.Stream() for _ in range(3)]
+        d_in = [torch.from_numpy(f).cuda() for f in frames]
+        torch.cuda.synchronize()
+        outs = [None] * 3
+        for rep in range(4):
+            for i, st in enumerate(streams):
+                with torch.cuda.stream(st):
+                    outs[i] = eng(d_in[i])
+        torch.cuda.synchronize()
+        for i in range(3):
+            assert (outs[i].cpu().numpy() == refs[i]).all(), i
+        # a ninth distinct stream is refused with a clear error instead of sharing a workspace
+        extra = [torch.cuda.Stream() for _ in range(8)]
+        with pytest.raises(ValueError, match="distinct streams"):
+            for st in extra:
+                with torch.cuda.stream(st):
+                    eng(d_in[0][:, :8, :16])
+        torch.cuda.synchronize()
 
 
 def test_call_compatible_single_pass(pass_cases):
