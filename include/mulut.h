@@ -163,7 +163,11 @@ int mulut_interp_bwd_f32(const float *d_weight, int n_rows, int up, char mode,
  *     pred = round(pred + rot90_back(InterpTorchBatch(weight_mode, up, mode, pad(rot90(x, r)))))
  * then  x' = round(clamp(pred / avg + bias, 0, 255))  - no rotated or padded copies are made.
  *   d_weights  n_modes raw parameter tables, float32 (n_rows, up^2) each
- *   d_x        float32 (B, C, h, w), integer-valued 0..255 (the reference's x * 255)
+ *   d_x        float32 (B, C, h, w), integer-valued 0..255 (the reference's x * 255).  PRECONDITION: the
+ *              kernel works on the integer grid and rounds every sample to the nearest integer first; the
+ *              reference flow only ever feeds integers (an input that is off by a float rounding error
+ *              gives the reference's result to ~1e-5).  Truly fractional inputs need the per-pass
+ *              entry points mulut_interp_fwd_f32 / _bwd_f32, which keep float fractions.
  *   d_out      float32 (B, C, h*up, w*up) = x'
  *   d_mask     uint8, same shape: 1 where 0 <= pred/avg + bias <= 255 (clamp passes the gradient)
  *   d_workspace  mulut_stage_workspace_bytes() bytes, 16-byte aligned, caller-owned: the forward

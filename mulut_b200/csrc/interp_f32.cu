@@ -403,7 +403,9 @@ stage_fwd_kernel(const __grid_constant__ StageF32Args a, float *__restrict__ out
                 for (int k = 0; k < 4; ++k) {
                     const int yy = clampi(y + a.taps.dy[m][r][k], 0, a.h - 1);
                     const int xx = clampi(x + a.taps.dx[m][r][k], 0, a.w - 1);
-                    t[k] = __ldg(plane + (size_t)yy * a.w + xx);
+                    // K4 works on the integer grid (see mulut.h): an input a rounding error away from k (x/255*255
+                    // computed with a reciprocal) is taken as k, as the reference's continuous interpolation would
+                    t[k] = rintf(__ldg(plane + (size_t)yy * a.w + xx));
                 }
                 Simplex s;
                 simplex_from_taps(t, a.interval, a.n_rows, s);
@@ -529,7 +531,9 @@ __device__ __forceinline__ void stage_bwd_body(const StageF32Args &a, const floa
                 for (int k = 0; k < 4; ++k) {
                     const int yy = clampi(y + a.taps.dy[m][r][k], 0, a.h - 1);
                     const int xx = clampi(x + a.taps.dx[m][r][k], 0, a.w - 1);
-                    t[k] = __ldg(plane + (size_t)yy * a.w + xx);
+                    // K4 works on the integer grid (see mulut.h): an input a rounding error away from k (x/255*255
+                    // computed with a reciprocal) is taken as k, as the reference's continuous interpolation would
+                    t[k] = rintf(__ldg(plane + (size_t)yy * a.w + xx));
                     sidx[k] = (yy - ty * K4_T + 2) * K4_P + (xx - tx * K4_T + 2);
                 }
                 Simplex s;

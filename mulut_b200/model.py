@@ -109,14 +109,14 @@ def fused_stage(x, weights, upscale, modes, avg, bias, interval=4, check_inputs=
     """x' = round(clamp(sum-with-per-pass-rounding / avg + bias, 0, 255)) for one stage.
 
     PRECONDITION: `x` is integer-valued (0..255 as float32) - what MuLUT.forward feeds every stage
-    ((k/255)*255 is exact in fp32 and every stage output is rounded).  K4 splits the samples into MSB / LSB
-    with integer arithmetic; a fractional input would be truncated where the reference's float
-    floor_divide / % (model.py:123-131) keeps the fraction.  check_inputs=True validates this (one device
-    synchronisation; not inside a CUDA-graph capture); the un-fused path (MuLUT(fused=False), K2/K3) accepts
-    any float input."""
+    ((k/255)*255 is exact in fp32 when the division is IEEE - a GPU `x / 255` through a reciprocal can be one
+    ulp off - and every stage output is rounded).  K4 works on the integer grid: it rounds every sample to
+    the nearest integer, where the reference's float floor_divide / % (model.py:123-131) keeps a fraction.
+    check_inputs=True rejects inputs further than 1e-3 from an integer (one device synchronisation; not
+    inside a CUDA-graph capture); the un-fused path (MuLUT(fused=False), K2/K3) accepts any float input."""
     modes = "".join(modes)
     if check_inputs and not torch.cuda.is_current_stream_capturing():
-        if bool((x.detach() != torch.round(x.detach())).any()):
+        if bool(((x.detach() - torch.round(x.detach())).abs() > 1e-3).any()):
             raise ValueError("fused_stage: the input is not integer-valued; use MuLUT(fused=False) for fractional inputs")
     for m in modes:
         if m not in ("s", "d", "y"):

@@ -33,6 +33,10 @@ __global__ void __launch_bounds__(1024) probe(uint32_t *out, unsigned long long 
             else if (OP == 12) { x[i] = __dp2a_lo(x[i], y, z); x[(i + 1) & 7] = x[(i + 1) & 7] * y + z; }   // IDP.2A + IMAD
             else if (OP == 13) { x[i] = __dp4a(x[i], y, z); asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(x[(i + 1) & 7]) : "r"(x[(i + 1) & 7]), "r"(y), "r"(z)); }   // IDP.4A + LOP3
             else if (OP == 14) { x[i] = __dp4a(x[i], y, z); x[(i + 1) & 7] = x[(i + 1) & 7] * y + z; }   // IDP.4A + IMAD
+            else if (OP == 16) x[i] = __vmaxu2(x[i], y);                       // VIMNMX.U16x2
+            else if (OP == 17) x[i] = __vadd2(x[i], y);                        // VIADD.16x2
+            else if (OP == 18) x[i] = __vimax3_u32(x[i], y, z);                // VIMNMX3
+            else if (OP == 19) { x[i] = __vmaxu2(x[i], y); x[(i + 1) & 7] = x[(i + 1) & 7] * y + z; }   // VIMNMX.U16x2 + IMAD
             else if (OP == 15) { asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(x[i]) : "r"(x[i]), "r"(y), "r"(z)); x[(i + 1) & 7] = x[(i + 1) & 7] * y + z; }   // LOP3 + IMAD
         }
     }
@@ -65,5 +69,6 @@ int main()
     run<0>("IMAD", 8); run<1>("IMAD.HI (+add)", 8); run<2>("SHF", 8); run<3>("VIMNMX", 8); run<4>("LOP3", 8);
     run<5>("IMAD.WIDE acc", 8); run<6>("IDP.4A", 8); run<7>("PRMT", 8); run<8>("IADD3", 8); run<9>("VIMNMX+IMAD", 16);
     run<10>("IDP.2A", 8); run<11>("IDP.2A+LOP3", 16); run<12>("IDP.2A+IMAD", 16); run<13>("IDP.4A+LOP3", 16); run<14>("IDP.4A+IMAD", 16); run<15>("LOP3+IMAD", 16);
+    run<16>("VIMNMX.U16x2", 8); run<17>("VIADD.16x2", 8); run<18>("VIMNMX3", 8); run<19>("VIMNMX.U16x2+IMAD", 16);
     return 0;
 }
