@@ -246,6 +246,8 @@ int mulut_host_free(void *p);
 #define MULUT_GB_LDS_U32       8   /* 4-byte loads from a shared-memory table                */
 #define MULUT_GB_QUAD_CELL256_3ROWS 9  /* 3 of the 4 64-B row-blocks of a 256-B cell, 4 lanes x 16 B (K1e) */
 #define MULUT_GB_QUAD_CELL256_4SECT 10 /* 4 of the 8 32-B sectors of a 256-B cell, one LDG.256 per lane   */
+#define MULUT_GB_BULK_CELL256   11 /* one cp.async.bulk (TMA unit) of a random 256-B cell per lane into a smem ring, then LDS */
+#define MULUT_GB_BULK_ROWS64X3  12 /* the same as three 64-B bulk copies (the row-blocks K1e reads)                     */
 int mulut_gather_bench(int device, int variant, size_t table_bytes, int iters_per_thread,
                        int blocks_per_sm, int threads_per_block, int repeats, double *out3);
 

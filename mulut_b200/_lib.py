@@ -21,7 +21,7 @@ PROF_KINDS = {"generic_stage": 0, "generic_last": 1, "smem_stage": 2, "combine":
 GB_VARIANTS = {
     "ldg_u8": 0, "ldg_u32": 1, "ldg_u128": 2, "quad_cell64": 3, "lds_u8": 4,
     "pair_cell64": 5, "oct_cell128": 6, "cpasync_cell64": 7, "lds_u32": 8,
-    "quad_cell256_3rows": 9, "quad_cell256_4sect": 10,
+    "quad_cell256_3rows": 9, "quad_cell256_4sect": 10, "bulk_cell256": 11, "bulk_rows64x3": 12,
 }
 
 # every symbol include/mulut.h declares: (restype, argtypes)

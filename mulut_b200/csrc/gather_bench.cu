@@ -4,6 +4,7 @@
 // denominators of the gather roofline (there is no datasheet figure) and the
 // evidence behind the layout choices in DESIGN.md.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace mulut {
 
@@ -70,6 +71,51 @@ __global__ void gather_kernel(const uint8_t *__restrict__ table, uint32_t n_entr
             __syncwarp();
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if constexpr (VARIANT == MULUT_GB_BULK_CELL256 || VARIANT == MULUT_GB_BULK_ROWS64X3) {
+        // the x4 cell fetch through the TMA unit instead of the L1TEX request path: every lane bulk-copies
+        // (cp.async.bulk -> UBLKCP) its random 256-B cell - whole, or as the three 64-B row-blocks K1e reads -
+        // into a per-warp ring in shared memory, one mbarrier per warp and stage counts the bytes; the lanes
+        // then read 3 x 16 B of their cell back with LDS.128
+        constexpr int DEPTH = 2;
+        const int warp = threadIdx.x >> 5;
+        uint8_t *ring = gb_smem + (size_t)warp * DEPTH * 8192;
+        uint64_t *bars = reinterpret_cast<uint64_t *>(gb_smem + (size_t)(blockDim.x >> 5) * DEPTH * 8192) + warp * DEPTH;
+        if (lane == 0) {
+            for (int d = 0; d < DEPTH; ++d) mbar_init(smem_u32(bars + d), 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        uint32_t sl = gtid * 40503u + 99u;
+        constexpr uint32_t per_lane = VARIANT == MULUT_GB_BULK_CELL256 ? 256u : 192u;
+        auto issue = [&](int stage) {
+            const uint32_t bar = smem_u32(bars + stage);
+            if (lane == 0) mbar_expect_tx(bar, 32u * per_lane);
+            __syncwarp();
+            const uint32_t cell = __umulhi(lcg(sl), n_entries);
+            const uint8_t *src = table + (size_t)cell * 256;
+            const uint32_t dst = smem_u32(ring + stage * 8192 + lane * 256);
+            if constexpr (VARIANT == MULUT_GB_BULK_CELL256) {
+                bulk_g2s(dst, src, 256u, bar);
+            } else {
+                const uint32_t mid = 64u + 64u * ((cell >> 3) & 1u);
+                bulk_g2s(dst, src, 64u, bar);
+                bulk_g2s(dst + 64u, src + mid, 64u, bar);
+                bulk_g2s(dst + 128u, src + 192, 64u, bar);
+            }
+        };
+        for (int p = 0; p < DEPTH - 1; ++p) issue(p);
+        for (int it = 0; it < iters; ++it) {
+            issue((it + DEPTH - 1) % DEPTH);
+            mbar_wait(smem_u32(bars + it % DEPTH), (uint32_t)(it / DEPTH) & 1u);
+            const uint4 *c = reinterpret_cast<const uint4 *>(ring + (it % DEPTH) * 8192 + lane * 256);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint4 v = c[(lane + 5 * k) & (per_lane / 16 - 1) & 7];
+                acc += v.x ^ v.y ^ v.z ^ v.w;
+            }
+            __syncwarp();
+        }
+        mbar_wait(smem_u32(bars + (iters + DEPTH - 2) % DEPTH), (uint32_t)((iters + DEPTH - 2) / DEPTH) & 1u);
     } else {
         const bool coop4 = VARIANT == MULUT_GB_QUAD_CELL64 || VARIANT == MULUT_GB_QUAD_CELL256_3ROWS ||
                            VARIANT == MULUT_GB_QUAD_CELL256_4SECT;
@@ -216,6 +262,16 @@ extern "C" int mulut_gather_bench(int device, int variant, size_t table_bytes, i
         if (smem > 200 * 1024) { set_error("too many threads for the cp.async ring"); rc = MULUT_E_BAD_ARG; break; }
         rc = run_variant<MULUT_GB_CPASYNC_CELL64>(d_table, (uint32_t)(table_bytes / 64), iters, blocks, threads, smem, d_sink, repeats, &ms);
         bytes_per_gather = 64; gathers_per_thread_iter = 1.0; break;   // one staged cell per lane per iteration
+    }
+    case MULUT_GB_BULK_CELL256:
+    case MULUT_GB_BULK_ROWS64X3: {
+        const size_t smem = (size_t)(threads / 32) * 2 * 8192 + (size_t)(threads / 32) * 2 * 8;
+        if (smem > 200 * 1024) { set_error("too many threads for the bulk-copy ring"); rc = MULUT_E_BAD_ARG; break; }
+        if (variant == MULUT_GB_BULK_CELL256)
+            rc = run_variant<MULUT_GB_BULK_CELL256>(d_table, (uint32_t)(table_bytes / 256), iters, blocks, threads, smem, d_sink, repeats, &ms);
+        else
+            rc = run_variant<MULUT_GB_BULK_ROWS64X3>(d_table, (uint32_t)(table_bytes / 256), iters, blocks, threads, smem, d_sink, repeats, &ms);
+        bytes_per_gather = variant == MULUT_GB_BULK_CELL256 ? 256 : 192; gathers_per_thread_iter = 1.0; break;   // one cell per lane per iteration
     }
     default:
         set_error("mulut_gather_bench: unknown variant %d", variant);

@@ -25,6 +25,10 @@ CASES = [
     ("oct_cell128", 24 << 20, "128-B lines, 8 lanes"),
     ("oct_cell128", 50 << 20, "x4 half-cells (128 B), three modes"),
     ("cpasync_cell64", 12 << 20, "x2 cell-major staged through smem with cp.async + 5 LDS"),
+    ("quad_cell256_3rows", 50 << 20, "x4 cell-major, three modes: K1e's three 64-B row-blocks by 4 lanes x LDG.128"),
+    ("quad_cell256_4sect", 50 << 20, "x4 sector layout, one LDG.256 per lane"),
+    ("bulk_cell256", 50 << 20, "x4 cell-major: one cp.async.bulk (TMA unit, UBLKCP) of the 256-B cell per lane -> smem ring -> LDS"),
+    ("bulk_rows64x3", 50 << 20, "x4 cell-major: three 64-B cp.async.bulk per lane -> smem ring -> LDS"),
     ("quad_cell64", 200 << 20, "beyond L2 (HBM gathers)"),
 ]
 
@@ -37,6 +41,8 @@ def run(device=0, iters=256, configs=((2, 512), (4, 256), (1, 1024))):
         best = None
         for bps, tpb in configs:
             if name == "cpasync_cell64" and tpb > 512:
+                continue
+            if name.startswith("bulk_") and tpb > 256:           # 16 KB of ring per warp
                 continue
             rc = L.mulut_gather_bench(device, _lib.GB_VARIANTS[name], table, iters, bps, tpb, 3, out)
             if rc != 0:

@@ -121,6 +121,42 @@ def pipeline_cases():
     print("ref_pipeline_cases:", len(meta))
 
 
+INTERVAL_CASES = [
+    # (name, H, W, C, stages, modes, scale, interval, img_seed, lut_seed): --interval other than the shipped 4
+    # (common/option.py `--interval`: q = 2^interval, L = 2^(8-interval) + 1) and scale 3 at several intervals
+    ("i5_x2_sdy_2st", 23, 31, 3, 2, "sdy", 2, 5, 120, 31),
+    ("i5_x3_sdy_2st", 14, 19, 3, 2, "sdy", 3, 5, 121, 32),
+    ("i5_x4_sdy_1st", 11, 13, 3, 1, "sdy", 4, 5, 122, 33),
+    ("i6_x2_sdy_2st", 17, 29, 3, 2, "sdy", 2, 6, 123, 34),
+    ("i7_x4_yd_2st", 9, 12, 3, 2, "yd", 4, 7, 124, 35),
+    ("i3_x2_sdy_2st", 13, 21, 3, 2, "sdy", 2, 3, 125, 36),
+    ("i4_x3_sdy_3st", 16, 11, 3, 3, "sdy", 3, 4, 126, 37),
+    ("i6_x1_s_2st", 8, 8, 1, 2, "s", 1, 6, 127, 38),
+]
+
+
+def interval_cases():
+    """Whole-pipeline cases at other intervals / scale 3, generated by the reference's own code."""
+    d = {}
+    meta = []
+    for name, H, W, C, stages, modes, scale, interval, iseed, lseed in INTERVAL_CASES:
+        img = case_image(H, W, C, iseed)
+        if C == 1:
+            img = img[:, :, 0]                       # grey input: the reference replicates it to 3 channels
+        luts = O.random_luts(lseed, stages, modes, scale, interval)
+        ref = R.ref_pipeline(img, luts, stages, list(modes), scale, interval)
+        mine = O.sr_pipeline(img, luts, stages, modes, scale, interval)
+        assert ref.dtype == np.uint8 and (ref == mine).all(), name
+        d["in_" + name] = img
+        d["out_" + name] = ref
+        meta.append(dict(name=name, H=H, W=W, C=C, stages=stages, modes=modes, scale=scale, interval=interval,
+                         img_seed=iseed, lut_seed=lseed))
+    np.savez_compressed(os.path.join(GOLD, "ref_interval_cases.npz"), **d)
+    with open(os.path.join(GOLD, "ref_interval_cases.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print("ref_interval_cases:", len(meta))
+
+
 def pass_cases():
     fn = R.test_lut_module().FourSimplexInterpFaster
     rng = np.random.default_rng(200)
@@ -224,6 +260,7 @@ def main():
     set5_hr_metrics()
     shipped_luts()
     pipeline_cases()
+    interval_cases()
     pass_cases()
     finetune_cases()
 

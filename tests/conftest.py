@@ -60,6 +60,14 @@ def pipeline_cases():
 
 
 @pytest.fixture(scope="session")
+def interval_cases():
+    """Reference-generated whole-pipeline cases at --interval 3/5/6/7 and scale 3 (oracle/make_golden.py)."""
+    data = np.load(os.path.join(GOLD, "ref_interval_cases.npz"))
+    meta = json.load(open(os.path.join(GOLD, "ref_interval_cases.json")))
+    return meta, data
+
+
+@pytest.fixture(scope="session")
 def pass_cases():
     data = np.load(os.path.join(GOLD, "ref_pass_cases.npz"))
     meta = json.load(open(os.path.join(GOLD, "ref_pass_cases.json")))

@@ -40,6 +40,20 @@ def test_reference_generated_fixtures(kernel, pipeline_cases):
         assert (out == ref).all(), (c["name"], int((out != ref).sum()))
 
 
+@pytest.mark.parametrize("kernel", [-1, 0, 1])
+def test_reference_generated_interval_fixtures(kernel, interval_cases):
+    """--interval 3/5/6/7 and scale 3 (no shipped model uses them): outputs of the reference's own code."""
+    from mulut_b200.infer import LutEngine
+    meta, data = interval_cases
+    for c in meta:
+        luts = O.random_luts(c["lut_seed"], c["stages"], c["modes"], c["scale"], c["interval"])
+        with LutEngine(luts, c["stages"], c["modes"], c["scale"], c["interval"], device=0, kernel=kernel) as eng:
+            out = eng(data["in_" + c["name"]])
+        ref = data["out_" + c["name"]]
+        assert out.shape == ref.shape, c["name"]
+        assert (out == ref).all(), (c["name"], int((out != ref).sum()))
+
+
 @pytest.mark.parametrize("kernel", list(KERNELS))
 @pytest.mark.parametrize("C", [1, 2, 3, 4, 5])
 def test_channel_counts_and_ragged_sizes(kernel, C):

@@ -36,6 +36,17 @@ def test_oracles_match_reference_pipeline_fixtures(pipeline_cases):
         assert (CO.sr_u8(img, luts, c["stages"], c["modes"], c["scale"], nthreads=1) == ref).all(), c["name"]
 
 
+def test_oracles_match_reference_interval_fixtures(interval_cases):
+    """--interval 3/5/6/7 and scale 3: numpy and C oracles against outputs of the reference's own code."""
+    meta, data = interval_cases
+    for c in meta:
+        luts = O.random_luts(c["lut_seed"], c["stages"], c["modes"], c["scale"], c["interval"])
+        img, ref = data["in_" + c["name"]], data["out_" + c["name"]]
+        assert (O.sr_pipeline(img, luts, c["stages"], c["modes"], c["scale"], c["interval"]) == ref).all(), c["name"]
+        img3 = img if img.ndim == 3 else np.stack([img] * 3, axis=2)
+        assert (CO.sr_u8(img3, luts, c["stages"], c["modes"], c["scale"], c["interval"]) == ref).all(), c["name"]
+
+
 def test_numpy_oracle_matches_reference_pass_fixtures(pass_cases):
     meta, data = pass_cases
     for c in meta:
