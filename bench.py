@@ -517,6 +517,7 @@ def main():
     r2, M = SCALE * SCALE, len(MODES)
     KINFO = {
         "smem_stage":    (60, 1, 1 + 2 * M, "lds_u8", "K1h/K1a: vertex gathers from the shared-memory LUT (K1h fetches the 60 algorithmic 1-byte vertices as 48 two-byte pairs)"),
+        "fused_stage":   (60, 1, 2, "lds_u8", "K1i: K1h (a-paired 16-bit table in shared memory: the 60 algorithmic 1-byte vertices as 48 two-byte gathers) with the mode combine and the stage epilogue fused; partial tiles are exchanged through an L2-resident ring"),
         "generic_stage": (60, 1, 2, "ldg_u32", "K0: vertex gathers through L1/L2"),
         "last_binned":   (60, r2, 1 + r2, "lds_u32", "K1f: 4-byte vertex-row gathers from shared-memory LUT slabs"),
         "last_tiled":    (60, r2, 1 + r2, "quad_cell256_3rows" if SCALE == 4 else "quad_cell64",

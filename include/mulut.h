@@ -120,7 +120,8 @@ long long mulut_launch_count(mulut_handle_t handle);
 #define MULUT_PROF_BIN_HIST       5   /* K1f preparation: histogram, plan, orphan list */
 #define MULUT_PROF_LAST_BINNED    6   /* stage_last2_binned_kernel (K1f)               */
 #define MULUT_PROF_BIN_ORPHANS    7   /* stage_generic_list_kernel: K1f's sparse bins  */
-#define MULUT_PROF_KINDS          8
+#define MULUT_PROF_FUSED_STAGE    8   /* stage_pair_fused_kernel (K1i): stage + mode combine + epilogue */
+#define MULUT_PROF_KINDS          9
 int mulut_profile_enable(mulut_handle_t handle, int on);
 int mulut_profile_read(mulut_handle_t handle, int kind, double *total_ms, long long *launches);
 

@@ -16,7 +16,7 @@ OK, E_BAD_MODE, E_BAD_ARG, E_CUDA, E_NOMEM, E_LUT_SMALL = 0, -1, -2, -3, -4, -5
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED, KERNEL_TILED_QUAD, KERNEL_TILED_CELL, KERNEL_TILED_BINNED = -1, 0, 1, 1, 2, 3
 
 PROF_KINDS = {"generic_stage": 0, "generic_last": 1, "smem_stage": 2, "combine": 3, "last_tiled": 4,
-              "bin_hist": 5, "last_binned": 6, "bin_orphans": 7}
+              "bin_hist": 5, "last_binned": 6, "bin_orphans": 7, "fused_stage": 8}
 
 GB_VARIANTS = {
     "ldg_u8": 0, "ldg_u32": 1, "ldg_u128": 2, "quad_cell64": 3, "lds_u8": 4,

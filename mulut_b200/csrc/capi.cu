@@ -41,6 +41,7 @@ struct Workspace {
     size_t bn_list_cap = 0;
     uint8_t *pitched = nullptr;             // staging copy of a stage input whose rows TMA cannot map in place
     size_t pitched_bytes = 0;
+    void *fused = nullptr;                  // K1i: L2-resident exchange ring + hand-off counters (kept zeroed by the kernel)
 };
 
 }  // namespace mulut
@@ -75,8 +76,14 @@ struct mulut_handle_s {
 };
 
 static int ws_reserve(Workspace &w, int stages, int n_modes, size_t frame_samples, bool want_partial,
-                      bool want_binned = false)
+                      bool want_binned = false, int fused_sms = 0)
 {
+    if (fused_sms > 0 && !w.fused) {        // never inside a stream capture (the caller checks): it synchronises
+        const size_t fb = stage1_fused_ws_bytes(fused_sms);
+        MULUT_CUDA(cudaMalloc(&w.fused, fb));
+        MULUT_CUDA(cudaMemset(w.fused, 0, fb));
+        MULUT_CUDA(cudaDeviceSynchronize());
+    }
     if (stages > 1 && w.img_bytes < frame_samples) {
         for (int i = 0; i < 2; ++i) { cudaFree(w.img[i]); w.img[i] = nullptr; }
         w.img_bytes = 0;
@@ -106,7 +113,7 @@ static int ws_reserve(Workspace &w, int stages, int n_modes, size_t frame_sample
 static void ws_free(Workspace &w)
 {
     cudaFree(w.img[0]); cudaFree(w.img[1]); cudaFree(w.partial); cudaFree(w.bn_ctl); cudaFree(w.bn_list);
-    cudaFree(w.pitched);
+    cudaFree(w.pitched); cudaFree(w.fused);
     w = Workspace();
 }
 
@@ -167,7 +174,14 @@ static int run_stages(mulut_handle_s *h, Workspace &w, const uint8_t *d_in, uint
         if (up == 1 && uses_tiled(h, up, C)) want_partial = true;
     }
     const bool want_binned = h->scale == 2 && h->interval == 4 && h->kernel != MULUT_KERNEL_GENERIC;
-    int rc = ws_reserve(w, h->stages, h->n_modes, samples, want_partial, want_binned);
+    // K1i (the opt-in fused stage kernel, MULUT_K1_FUSED=1) needs its exchange ring; it is not used (nor allocated)
+    // inside a stream capture.  The int16 partial planes of K1h + K1b are reserved when that path is taken.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
+    const bool capturing = cap != cudaStreamCaptureStatusNone;
+    const bool want_fused = stage1_fused_enabled() && want_partial && h->interval == 4 && C <= 4 && !capturing &&
+                            h->kernel != MULUT_KERNEL_TILED_QUAD && h->kernel != MULUT_KERNEL_TILED_CELL;
+    int rc = ws_reserve(w, h->stages, h->n_modes, samples, false, want_binned, want_fused ? h->num_sms : 0);
     if (rc) return rc;
 
     const uint8_t *cur = d_in;
@@ -225,8 +239,21 @@ static int run_stages(mulut_handle_s *h, Workspace &w, const uint8_t *d_in, uint
                 for (int m = 0; m < h->n_modes; ++m) nx.lut_slab[m] = h->lut_slab[m];
                 if (binned_supported(nx, h->scale)) pa = binned_plan_args(nx, w.bn_ctl, w.bn_list, w.bn_list_cap);
             }
-            done = launch_stage_tiled_ws(a, up, w.partial, stream, &launches, &h->prof, owner_only, &pa);
-            if (done < 0) return done;
+            done = 1;
+            if (up == 1 && a.in_tma && w.fused && !capturing) {            // K1i: stage + combine (+ plan) in one kernel
+                h->prof.begin(MULUT_PROF_FUSED_STAGE, stream);
+                done = launch_stage1_fused(a, w.fused, pa.ctl ? &pa : nullptr, stream);
+                if (done == 0) { h->prof.end(stream); launches = 1; } else h->prof.cancel();
+                if (done < 0) return done;
+            }
+            if (done == 1) {
+                if (up == 1) {                                             // K1h / K1a + K1b: int16 partial planes
+                    rc = ws_reserve(w, h->stages, h->n_modes, samples, true, false);
+                    if (rc) return rc;
+                }
+                done = launch_stage_tiled_ws(a, up, w.partial, stream, &launches, &h->prof, owner_only, &pa);
+                if (done < 0) return done;
+            }
             planned = done == 0 && pa.ctl != nullptr && up == 1;
             h->launches += launches;
         }
@@ -458,7 +485,8 @@ int mulut_reserve(mulut_handle_t h, int N, int H, int W, int C)
         }
         Workspace &w = h->dev_ws[i];
         rc = ws_reserve(w, h->stages, h->n_modes, (size_t)N * H * W * C, h->interval == 4,
-                        h->scale == 2 && h->interval == 4);
+                        h->scale == 2 && h->interval == 4,
+                        (stage1_fused_enabled() && h->interval == 4 && C <= 4) ? h->num_sms : 0);
         if (rc) return rc;
         // the pitched staging copy of frames TMA cannot map in place (sized for the worst case: the caller's
         // pointer may turn out to be misaligned even when W*C is a multiple of 16)

@@ -47,6 +47,7 @@ struct Prof {
         ++n;
         open = false;
     }
+    void cancel() { open = false; }       // begin() without a launch: drop the record
     bool open = false;
 };
 
@@ -68,6 +69,12 @@ bool stage1_tma_supported(const StageArgs &a, int up);
 size_t stage1_pair_bytes();
 int build_pair_table(const int8_t *d_lut_vertex_major, uint8_t *d_pair, cudaStream_t stream);
 int launch_stage1_tma(const StageArgs &a, int16_t *partial, cudaStream_t stream);
+// K1i: K1h with the mode combine, the stage epilogue and K1f's histogram + plan fused (cooperative launch; the
+// modes exchange partial tiles through an L2-resident ring).  ws: stage1_fused_ws_bytes() of zeroed device memory.
+// Returns MULUT_OK, an error (< 0) or +1 (not applicable: run launch_stage1_tma + K1b).
+bool stage1_fused_enabled();            // MULUT_K1_FUSED=1 (opt-in; read on every call)
+size_t stage1_fused_ws_bytes(int num_sms);
+int launch_stage1_fused(const StageArgs &a, void *ws, const BinPlanArgs *plan, cudaStream_t stream);
 
 // K1f, the binned shared-memory kernel for the up = 2 last stage (infer_binned.cu).
 // binned_supported: configuration + TMA preconditions (16-byte aligned frames, W*C % 16 == 0).

@@ -176,10 +176,13 @@ def test_auto_picks_binned_for_large_launches_and_host_path_agrees():
 @pytest.mark.parametrize("scale,stages,modes,shape", [(1, 2, "sdy", (2, 70, 112, 3)), (1, 3, "ds", (1, 33, 96, 1)),
                                                       (4, 2, "sdy", (2, 45, 80, 3)), (3, 2, "ys", (1, 64, 160, 3)),
                                                       (1, 1, "y", (1, 2, 16, 3))])
-def test_tma_stage_kernel_k1g(scale, stages, modes, shape):
-    """K1g (TMA tile ring + shared-memory LUT) serves every up = 1 stage of TMA-mappable frames,
-    whatever the last stage is: scales 1/3/4 pair it with K1b-as-last-stage, K0 or K1e."""
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_tma_stage_kernel_k1g(scale, stages, modes, shape, fused, monkeypatch):
+    """The TMA-fed shared-memory stage kernels serve every up = 1 stage of TMA-mappable frames, whatever the
+    last stage is (scales 1/3/4 pair them with an up = 1 last stage, K0 or K1e): K1h + K1b (the default) and,
+    with MULUT_K1_FUSED=1, K1i (stage + mode combine + epilogue in one cooperative kernel)."""
     import torch
+    monkeypatch.setenv("MULUT_K1_FUSED", fused)
     from mulut_b200.infer import LutEngine
     rng = np.random.default_rng(sum(shape) + scale)
     luts = O.random_luts(50 + scale, stages, modes, scale)
@@ -190,10 +193,44 @@ def test_tma_stage_kernel_k1g(scale, stages, modes, shape):
         out = eng(torch.from_numpy(frames).cuda()).cpu().numpy()
         prof = eng.profile_read()
     if stages > 1 or scale == 1:
-        assert "smem_stage" in prof, prof
+        if fused == "1":
+            assert "fused_stage" in prof and "smem_stage" not in prof and "combine" not in prof, prof
+        else:
+            assert "smem_stage" in prof and "combine" in prof and "fused_stage" not in prof, prof
     assert (out == ref).all(), (scale, stages, modes, int((out != ref).sum()))
     with LutEngine(luts, stages, modes, scale, 4, device=0, kernel=1) as eng:  # K1a (no TMA) gives the same bytes
         assert (eng(torch.from_numpy(frames).cuda()).cpu().numpy() == ref).all()
+
+
+@pytest.mark.parametrize("modes,stages,scale", [("sdy", 2, 2), ("sd", 3, 2), ("y", 2, 2), ("sdys", 2, 1)])
+def test_fused_stage_kernel_many_tiles_and_back_to_back_launches(modes, stages, scale, monkeypatch):
+    """K1i (opt-in: MULUT_K1_FUSED=1) over enough tiles that every stream reuses its exchange slots many times,
+    with 1 to 4 modes, launched back to back (the kernel must leave its hand-off counters zeroed) and from two
+    streams of one handle."""
+    import torch
+    from mulut_b200.infer import LutEngine
+    monkeypatch.setenv("MULUT_K1_FUSED", "1")
+    rng = np.random.default_rng(len(modes) * 10 + stages)
+    luts = O.random_luts(70 + stages, stages, modes, scale)
+    frames = rng.integers(0, 256, (3, 600, 1120, 3), dtype=np.uint8)       # 1197 stage tiles: ~12 per stream
+    ref = CO.sr_u8(frames, luts, stages, modes, scale)
+    with LutEngine(luts, stages, modes, scale, 4, device=0) as eng:
+        d = torch.from_numpy(frames).cuda()
+        eng.profile(True)
+        outs = [eng(d) for _ in range(3)]
+        prof = eng.profile_read()
+        eng.profile(False)
+        assert "fused_stage" in prof and "combine" not in prof, prof
+        for o in outs:
+            assert (o.cpu().numpy() == ref).all()
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            o2 = eng(d)
+        o1 = eng(d)
+        torch.cuda.synchronize()
+        assert (o1.cpu().numpy() == ref).all() and (o2.cpu().numpy() == ref).all()
+        small = rng.integers(0, 256, (1, 5, 16, 3), dtype=np.uint8)          # fewer tiles than streams
+        assert (eng(torch.from_numpy(small).cuda()).cpu().numpy() == CO.sr_u8(small, luts, stages, modes, scale)).all()
 
 
 def test_binned_sparse_resident_bins_walk_many_tiles(monkeypatch):
