@@ -214,7 +214,6 @@ __device__ __forceinline__ void binned_mode(const uint8_t *__restrict__ sp, uint
 {
     constexpr int P = BN_BOXW;
     constexpr uint32_t SA = BN_SLAB_BYTES, SB = 289u * 4u, SC = 17u * 4u, SD = 4u;
-    constexpr uint32_t KM = 0x0FFFFFFFu;
     const uint32_t k0c = (t0 << 28) | SA;          // fraction in the top nibble, byte stride below
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -223,11 +222,18 @@ __device__ __forceinline__ void binned_mode(const uint8_t *__restrict__ sp, uint
         const uint32_t t3 = sp[bn_tap_off(MODE, r, 3, true) * P + bn_tap_off(MODE, r, 3, false) * CT];
         const uint32_t v0 = (t1 >> 4) * SB + (t2 >> 4) * SC + (t3 >> 4) * SD;
         // (forcing these through mad.lo to unload the ALU pipe measured 4 % slower: ptxas loses the shared shifts)
+        // (the keys themselves through mad.lo: ptxas turns them into LEA on the ALU pipe again, 3.60 ms)
         uint32_t k0 = k0c, k1 = (t1 << 28) | SB, k2 = (t2 << 28) | SC, k3 = (t3 << 28) | SD;
         sort4_desc(k0, k1, k2, k3);
         const uint32_t f1 = k0 >> 28, f2 = k1 >> 28, f3 = k2 >> 28, f4 = k3 >> 28;
-        const uint32_t v1 = v0 + (k0 & KM), v2 = v1 + (k1 & KM);
-        const uint32_t v4 = v0 + (SA + SB + SC + SD), v3 = v4 - (k3 & KM);
+        // stride = key - (f << 28) as ONE IMAD (f * 0xF0000000 + key) instead of a LOP3 mask: the kernel is bound
+        // by the ALU pipe (72 %), the FMA pipe has room - 3.66 -> 3.57 ms on cfg 2 although it costs three more adds
+        uint32_t s1, s2, s4;
+        asm("mad.lo.u32 %0, %1, 0xF0000000, %2;" : "=r"(s1) : "r"(f1), "r"(k0));
+        asm("mad.lo.u32 %0, %1, 0xF0000000, %2;" : "=r"(s2) : "r"(f2), "r"(k1));
+        asm("mad.lo.u32 %0, %1, 0xF0000000, %2;" : "=r"(s4) : "r"(f4), "r"(k3));
+        const uint32_t v1 = v0 + s1, v2 = v1 + s2;
+        const uint32_t v4 = v0 + (SA + SB + SC + SD), v3 = v4 - s4;
         const uint32_t r0 = *reinterpret_cast<const uint32_t *>(lut_a + v0);
         const uint32_t r1 = *reinterpret_cast<const uint32_t *>(lut_a + v1);
         const uint32_t r2 = *reinterpret_cast<const uint32_t *>(lut_a + v2);
