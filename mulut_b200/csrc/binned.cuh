@@ -8,7 +8,10 @@
 namespace mulut {
 
 constexpr int BN_TW = 96;                       // tile width, byte columns (multiple of C for C <= 4)
-constexpr int BN_TH = 16;                       // tile rows
+#ifndef MULUT_BN_TH
+#define MULUT_BN_TH 16
+#endif
+constexpr int BN_TH = MULUT_BN_TH;              // tile rows
 constexpr int BN_BINS = 8;
 
 struct BinCtl {                         // device, 256 B, zeroed before every launch
@@ -33,7 +36,10 @@ struct BinPlanArgs {                    // what the plan needs besides the histo
 // A bin is worth a resident CTA group only if its samples outweigh the fixed cost of
 // walking every tile once more (scan + barriers); sparse bins go to a list that the
 // generic L2-gather kernel finishes (stage_generic_list_kernel).  Costs in SM cycles.
-constexpr unsigned long long BN_CV = 1050;      // per visit of a 96 x 16 tile (fit of tools/bn_timing.py's per-bin totals: 975-1085)
+#ifndef MULUT_BN_CV
+#define MULUT_BN_CV 1050
+#endif
+constexpr unsigned long long BN_CV = MULUT_BN_CV;   // per visit of a 96 x 16 tile (fit of tools/bn_timing.py's per-bin totals: 975-1085)
 constexpr unsigned long long BN_CS = 10;        // per sample interpolated from shared memory (same fit: 10.1-10.2)
 constexpr unsigned long long BN_CG = 26;        // per sample interpolated by the list kernel
 

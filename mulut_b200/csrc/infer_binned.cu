@@ -53,15 +53,30 @@ constexpr int BN_HX = 16;                       // box column of the tile's firs
 constexpr int BN_BOXW = 128;                    // HX + TW + 2*C rounded up to 16 B (C <= 4)
 constexpr int BN_BOXH = BN_TH + 4;
 constexpr int BN_SLOT = BN_BOXW * BN_BOXH;      // 2560 B per ring slot, 128-B aligned
-constexpr int BN_RING = 6;
-constexpr int BN_AHEAD = 2;                     // TMA prefetch distance in tiles
+#ifndef MULUT_BN_RING
+#define MULUT_BN_RING 6
+#endif
+#ifndef MULUT_BN_AHEAD
+#define MULUT_BN_AHEAD 2
+#endif
+#ifndef MULUT_BN_GROUPS
+#define MULUT_BN_GROUPS 2
+#endif
+#ifndef MULUT_BN_GT
+#define MULUT_BN_GT 384
+#endif
+#ifndef MULUT_BN_QCAP
+#define MULUT_BN_QCAP 4096
+#endif
+constexpr int BN_RING = MULUT_BN_RING;
+constexpr int BN_AHEAD = MULUT_BN_AHEAD;        // TMA prefetch distance in tiles
 constexpr int BN_CARRY = BN_RING - BN_AHEAD - 1;   // tiles a queue entry may outlive its scan
-constexpr int BN_GROUPS = 2;                    // independent tile pipelines per CTA (own ring, queue, named barrier): one
+constexpr int BN_GROUPS = MULUT_BN_GROUPS;      // independent tile pipelines per CTA (own ring, queue, named barrier): one
                                                 // group's scan / barrier / TMA wait hides behind the other's rounds
-constexpr int BN_GT = 384;                      // threads per group
+constexpr int BN_GT = MULUT_BN_GT;              // threads per group
 constexpr int BN_THREADS = BN_GROUPS * BN_GT;   // 24 warps (1024 threads fit at 62 registers but measured no faster)
-constexpr int BN_SCAN_THREADS = BN_GT;          // TW/4 x TH words of a tile, one per scanning thread
-constexpr int BN_QCAP = 4096;                   // queue capacity per group: power of two > (GT - 1 + TW*TH) + TW*TH
+constexpr int BN_SCAN_THREADS = BN_TW / 4 * BN_TH;   // TW/4 x TH words of a tile, one per scanning thread
+constexpr int BN_QCAP = MULUT_BN_QCAP;          // queue capacity per group: power of two > (GT - 1 + TW*TH) + TW*TH
 constexpr int BN_SLAB_WORDS = 4916;             // 17^3 = 4913 rows, padded so a slab is a 16-B multiple
 constexpr int BN_SLAB_BYTES = BN_SLAB_WORDS * 4;
 constexpr int BN_BIN_BYTES = 3 * BN_SLAB_BYTES; // slabs 2b, 2b+1, 2b+2 of one mode
@@ -220,7 +235,16 @@ __device__ __forceinline__ void binned_mode(const uint8_t *__restrict__ sp, uint
         const uint32_t t1 = sp[bn_tap_off(MODE, r, 1, true) * P + bn_tap_off(MODE, r, 1, false) * CT];
         const uint32_t t2 = sp[bn_tap_off(MODE, r, 2, true) * P + bn_tap_off(MODE, r, 2, false) * CT];
         const uint32_t t3 = sp[bn_tap_off(MODE, r, 3, true) * P + bn_tap_off(MODE, r, 3, false) * CT];
-        const uint32_t v0 = (t1 >> 4) * SB + (t2 >> 4) * SC + (t3 >> 4) * SD;
+        // base vertex through three IMADs on the m = t >> 4 the taps share (left to itself the compiler packs
+        // two of them for a dp2a with PRMTs and masks the third out of t >> 2: all on the ALU pipe; 3.57 -> 3.48 ms)
+        uint32_t v0;
+        {
+            const uint32_t m1 = t1 >> 4, m2 = t2 >> 4, m3 = t3 >> 4;
+            uint32_t x;
+            asm("mad.lo.u32 %0, %1, %2, 0;" : "=r"(x) : "r"(m3), "r"(SD));
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(x) : "r"(m2), "r"(SC), "r"(x));
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(v0) : "r"(m1), "r"(SB), "r"(x));
+        }
         // (forcing these through mad.lo to unload the ALU pipe measured 4 % slower: ptxas loses the shared shifts)
         // (the keys themselves through mad.lo: ptxas turns them into LEA on the ALU pipe again, 3.60 ms)
         uint32_t k0 = k0c, k1 = (t1 << 28) | SB, k2 = (t2 << 28) | SC, k3 = (t3 << 28) | SD;
@@ -241,6 +265,8 @@ __device__ __forceinline__ void binned_mode(const uint8_t *__restrict__ sp, uint
         const uint32_t r4 = *reinterpret_cast<const uint32_t *>(lut_a + v4);
         const uint32_t w0 = 16u - f1, w1 = f1 - f2, w2 = f2 - f3, w3 = f3 - f4, w4 = f4;
         constexpr uint32_t EM = 0x00FF00FFu;
+        // (the even outputs through IDP.2A.LO/HI with the bare weight - no mask, two FMA-pipe ops - measured 3.70 ms
+        // against 3.57; the weights through mad.lo 3.60)
         AE[r] += (r0 & EM) * w0 + (r1 & EM) * w1 + (r2 & EM) * w2 + (r3 & EM) * w3 + (r4 & EM) * w4;
         AO[r] += (unsigned long long)r0 * w0 + (unsigned long long)r1 * w1 + (unsigned long long)r2 * w2 +
                  (unsigned long long)r3 * w3 + (unsigned long long)r4 * w4;
