@@ -595,13 +595,17 @@ stage_last2_cell_kernel(const __grid_constant__ StageArgs a)
 // or tap b has the larger fraction): 3 x (4 lanes x LDG.128).
 //   byte[cell*256 + l*64 + q*16 + i*4 + cd] = LUT[v(l,cd)][col(q,i)] + 128
 // ---------------------------------------------------------------------------
-__host__ __device__ constexpr int orbit_col(int q, int i)
-{
-    int u = q == 3 ? 1 : 0, v = q == 3 ? 1 : q;        // orbit starts (0,0),(0,1),(0,2),(1,1)
-    for (int k = 0; k < i; ++k) { int t = u; u = v; v = 3 - t; }
-    return u * 4 + v;
-}
+// up = 3 (K1e3) uses the same 256-B cells and the same fetch: the 3x3 block has a corner orbit (lane 0), an edge
+// orbit (lane 1) and the rotation-invariant centre (lane 2, the same column in all four words, so that every
+// rotation adds it to every position of the lane: any one of the four accumulators holds it); lane 3 carries
+// nothing.  7 of 16 table bytes are padding: the price of reusing the x4 gather, which is bound by requests
+// and L2 bytes per CELL, not by the bytes used.
+template <int UP>
+__host__ __device__ constexpr int orbit_start_u(int q) { return UP == 4 ? (q == 3 ? 1 : 0) : (q == 2 ? 1 : 0); }
+template <int UP>
+__host__ __device__ constexpr int orbit_start_v(int q) { return UP == 4 ? (q == 3 ? 1 : q) : (q == 2 ? 1 : q == 3 ? 1 : q); }
 
+template <int UP>
 __global__ void build_cell_major4_kernel(const int8_t *__restrict__ lut, uint8_t *__restrict__ cells)
 {
     const size_t total = (size_t)65536 * 256;
@@ -611,13 +615,13 @@ __global__ void build_cell_major4_kernel(const int8_t *__restrict__ lut, uint8_t
         const int cell = (int)(idx >> 8);
         const int ma = cell >> 12, mb = (cell >> 8) & 15, mc = (cell >> 4) & 15, md = cell & 15;
         const int v = (ma + (l >> 1)) * 4913 + (mb + (l & 1)) * 289 + (mc + (cd >> 1)) * 17 + (md + (cd & 1));
-        int u = q == 3 ? 1 : 0, w = q == 3 ? 1 : q;
-        for (int k = 0; k < i; ++k) { int t = u; u = w; w = 3 - t; }
-        cells[idx] = (uint8_t)((int)lut[(size_t)v * 16 + u * 4 + w] + 128);
+        int u = orbit_start_u<UP>(q), w = orbit_start_v<UP>(q);
+        for (int k = 0; k < i; ++k) { int t = u; u = w; w = UP - 1 - t; }
+        cells[idx] = (UP == 3 && q == 3) ? (uint8_t)128 : (uint8_t)((int)lut[(size_t)v * (UP * UP) + u * UP + w] + 128);
     }
 }
 
-constexpr int Q4_OP = 4 * TWB;
+template <int UP> __host__ __device__ constexpr int q4_op() { return UP * TWB; }
 
 template <char MODE, int CT>
 __device__ __forceinline__ void quad4_mode(const uint8_t *__restrict__ sp, int C,
@@ -669,14 +673,16 @@ __device__ __forceinline__ void quad4_mode(const uint8_t *__restrict__ sp, int C
     }
 }
 
-template <int CT>
+template <int CT, int UP>
 __global__ void __launch_bounds__(Q2_THREADS, 2)
 stage_last4_quad_kernel(const __grid_constant__ StageArgs a)
 {
+    static_assert(UP == 3 || UP == 4, "K1e serves up = 4 and, with padded cells, up = 3");
     constexpr int P = tile_pitch<CT>();
+    constexpr int Q4_OP = q4_op<UP>();
     extern __shared__ __align__(16) uint8_t q4_smem[];
-    uint8_t *s_out = q4_smem;                                  // 4*TH x 4*TWB bytes
-    uint8_t *s_in = q4_smem + 4 * Q2_TH * Q4_OP;
+    uint8_t *s_out = q4_smem;                                  // UP*TH x UP*TWB bytes
+    uint8_t *s_in = q4_smem + UP * Q2_TH * Q4_OP;
     __shared__ __align__(8) uint16_t s_sel[1024];
 
     build_selector_table(s_sel);
@@ -690,18 +696,20 @@ stage_last4_quad_kernel(const __grid_constant__ StageArgs a)
     const int rp = warp / 3;
     const int ql = lane & 3;
     const int cols = TWB + 4 * C;
-    const int oWC = 4 * WC;
+    const int oWC = UP * WC;
     const uint32_t bias_total = (uint32_t)a.n_modes * 4u * 2048u;
     const uint32_t den = 16u * a.n_modes;
     const uint32_t magic = rhe_magic(den);
-    // my orbit's four sub-pixel positions (u,v), in rotation order
+    // my orbit's four sub-pixel positions (u,v), in rotation order (up = 3: lane 2 holds the centre in every
+    // word - only word 0 is stored - and lane 3 nothing)
     int pu[4], pv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        int u = ql == 3 ? 1 : 0, v = ql == 3 ? 1 : ql;
-        for (int k = 0; k < i; ++k) { int t = u; u = v; v = 3 - t; }
+        int u = UP == 4 ? (ql == 3 ? 1 : 0) : (ql >= 2 ? 1 : 0), v = UP == 4 ? (ql == 3 ? 1 : ql) : (ql >= 2 ? 1 : ql);
+        for (int k = 0; k < i; ++k) { int t = u; u = v; v = UP - 1 - t; }
         pu[i] = u; pv[i] = v;
     }
+    const int n_store = UP == 4 ? 4 : (ql < 2 ? 4 : ql == 2 ? 1 : 0);     // accumulators of this lane that are outputs
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int tx = (int)(tile % tiles_x);
@@ -735,16 +743,16 @@ stage_last4_quad_kernel(const __grid_constant__ StageArgs a)
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const int sx = (lx & ~3) + s;                          // local byte column of sample s
-                uint8_t *so = s_out + (4 * ly) * Q4_OP + sx + 3 * C * (sx / C);
+                uint8_t *so = s_out + (UP * ly) * Q4_OP + sx + (UP - 1) * C * (sx / C);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int S = (int)acc[s][i] - (int)bias_total;
-                    so[pu[i] * Q4_OP + pv[i] * C] = (uint8_t)rhe_div_clamp_u8_magic(S, den, magic);
+                    if (i < n_store) so[pu[i] * Q4_OP + pv[i] * C] = (uint8_t)rhe_div_clamp_u8_magic(S, den, magic);
                 }
             }
         }
         __syncthreads();
-        store_out_tile<4>(s_out, a.out, n, a.H, oWC, y0, X0);
+        store_out_tile<UP>(s_out, a.out, n, a.H, oWC, y0, X0);
     }
 }
 
@@ -772,7 +780,7 @@ size_t cell_major_bytes(int up)
 {
     if (up == 1) return LUT1_SMEM + stage1_pair_bytes();     // [padded int8 table | a-paired 16-bit table of K1h]
     if (up == 2) return (size_t)65536 * 64;
-    if (up == 4) return (size_t)65536 * 256;
+    if (up == 4 || up == 3) return (size_t)65536 * 256;     // up = 3: the x4 cell with 9 of 16 columns used (K1e3)
     return 0;
 }
 
@@ -788,8 +796,9 @@ int build_cell_major(const int8_t *d_lut, uint8_t *d_alt, int up, cudaStream_t s
         MULUT_CUDA(cudaGetLastError());
         return MULUT_OK;
     }
-    if (up == 4) {
-        build_cell_major4_kernel<<<2048, 256, 0, stream>>>(d_lut, d_alt);
+    if (up == 4 || up == 3) {
+        if (up == 4) build_cell_major4_kernel<4><<<2048, 256, 0, stream>>>(d_lut, d_alt);
+        else build_cell_major4_kernel<3><<<2048, 256, 0, stream>>>(d_lut, d_alt);
         MULUT_CUDA(cudaGetLastError());
         return MULUT_OK;
     }
@@ -798,7 +807,7 @@ int build_cell_major(const int8_t *d_lut, uint8_t *d_alt, int up, cudaStream_t s
 
 bool tiled_supported(int up, int interval, int n_modes)
 {
-    return interval == 4 && n_modes >= 1 && (up == 1 || up == 2 || up == 4);
+    return interval == 4 && n_modes >= 1 && up >= 1 && up <= 4;
 }
 
 // ---------------------------------------------------------------------------
@@ -855,23 +864,23 @@ static int launch_quad_stage(const StageArgs &a, bool owner_only, cudaStream_t s
     return MULUT_OK;
 }
 
-template <int CT>
+template <int CT, int UP>
 static int launch_quad4_stage(const StageArgs &a, cudaStream_t stream)
 {
     constexpr int P = tile_pitch<CT>();
-    const size_t smem = (size_t)4 * Q2_TH * Q4_OP + (size_t)(Q2_TH + 4) * P;
+    const size_t smem = (size_t)UP * Q2_TH * q4_op<UP>() + (size_t)(Q2_TH + 4) * P;
     {
-        int rc = set_smem(stage_last4_quad_kernel<CT>, smem);
+        int rc = set_smem(stage_last4_quad_kernel<CT, UP>, smem);
         if (rc) return rc;
     }
     int per_sm = 0;
-    MULUT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_last4_quad_kernel<CT>, Q2_THREADS, smem));
+    MULUT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_last4_quad_kernel<CT, UP>, Q2_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     const int WC = a.W * a.C;
     const long long n_tiles = (long long)a.N * ((a.H + Q2_TH - 1) / Q2_TH) * ((WC + TWB - 1) / TWB);
     long long grid = (long long)per_sm * a.num_sms;
     if (grid > n_tiles) grid = n_tiles;
-    stage_last4_quad_kernel<CT><<<(unsigned)grid, Q2_THREADS, smem, stream>>>(a);
+    stage_last4_quad_kernel<CT, UP><<<(unsigned)grid, Q2_THREADS, smem, stream>>>(a);
     MULUT_CUDA(cudaGetLastError());
     return MULUT_OK;
 }
@@ -914,9 +923,13 @@ int launch_stage_tiled_ws(const StageArgs &a, int up, int16_t *partial, cudaStre
     prof->begin(MULUT_PROF_LAST_TILED, stream);
     int rc;
     if (up == 4)
-        rc = a.C == 3 ? launch_quad4_stage<3>(a, stream)
-           : a.C == 1 ? launch_quad4_stage<1>(a, stream)
-                      : launch_quad4_stage<0>(a, stream);
+        rc = a.C == 3 ? launch_quad4_stage<3, 4>(a, stream)
+           : a.C == 1 ? launch_quad4_stage<1, 4>(a, stream)
+                      : launch_quad4_stage<0, 4>(a, stream);
+    else if (up == 3)
+        rc = a.C == 3 ? launch_quad4_stage<3, 3>(a, stream)
+           : a.C == 1 ? launch_quad4_stage<1, 3>(a, stream)
+                      : launch_quad4_stage<0, 3>(a, stream);
     else
         rc = a.C == 3 ? launch_quad_stage<3>(a, owner_only, stream)
            : a.C == 1 ? launch_quad_stage<1>(a, owner_only, stream)

@@ -54,6 +54,39 @@ def test_reference_generated_interval_fixtures(kernel, interval_cases):
         assert (out == ref).all(), (c["name"], int((out != ref).sum()))
 
 
+@pytest.mark.parametrize("interval,scale,stages,modes", [(5, 2, 2, "sdy"), (6, 4, 2, "sdy"), (7, 3, 2, "yd"), (5, 1, 3, "sdy"),
+                                                         (6, 3, 1, "s"), (5, 4, 2, "sdy")])
+def test_small_table_intervals_at_size(interval, scale, stages, modes):
+    """Intervals 5-7 at a few hundred thousand samples per launch (K0 serves them): bit-exact against the C oracle."""
+    import torch
+    from mulut_b200.infer import LutEngine
+    rng = np.random.default_rng(interval * 10 + scale)
+    luts = O.random_luts(80 + interval, stages, modes, scale, interval)
+    frames = rng.integers(0, 256, (2, 211, 317, 3), dtype=np.uint8)           # 401 k samples
+    ref = CO.sr_u8(frames, luts, stages, modes, scale, interval)
+    with LutEngine(luts, stages, modes, scale, interval, device=0) as eng:
+        out = eng(torch.from_numpy(frames).cuda()).cpu().numpy()
+    assert (out == ref).all(), (interval, scale, int((out != ref).sum()))
+
+
+def test_full_size_x3_matches_c_oracle():
+    """Scale 3 at the shipped interval: K1h + K1b + K1e3 (the x4 cell kernel on 9-of-16-column cells), one
+    640x360 frame -> 1920x1080, bit-exact against the C oracle for AUTO, the tiled selection and K0."""
+    import torch
+    from mulut_b200.infer import LutEngine
+    rng = np.random.default_rng(303)
+    luts = O.random_luts(33, 2, "sdy", 3)
+    frame = rng.integers(0, 256, (2, 360, 640, 3), dtype=np.uint8)
+    ref = CO.sr_u8(frame, luts, 2, "sdy", 3)
+    for kernel in (-1, 1, 0):
+        with LutEngine(luts, 2, "sdy", 3, 4, device=0, kernel=kernel) as eng:
+            eng.profile(True)
+            out = eng(torch.from_numpy(frame).cuda()).cpu().numpy()
+            prof = eng.profile_read()
+        assert ("last_tiled" in prof) == (kernel != 0), (kernel, list(prof))
+        assert out.shape == (2, 1080, 1920, 3) and (out == ref).all(), (kernel, int((out != ref).sum()))
+
+
 @pytest.mark.parametrize("kernel", list(KERNELS))
 @pytest.mark.parametrize("C", [1, 2, 3, 4, 5])
 def test_channel_counts_and_ragged_sizes(kernel, C):
