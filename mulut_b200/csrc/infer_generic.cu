@@ -31,6 +31,48 @@ __device__ __forceinline__ void load_row(const int8_t *__restrict__ p, int (&v)[
     }
 }
 
+// rotated tap offset of (mode, rotation r, tap k), compile-time (same rule as common.cuh::build_tap_table)
+__host__ __device__ constexpr int k0_tap_off(char mode, int r, int k, bool want_dy)
+{
+    int dy = mode == 's' ? (k >> 1) : mode == 'd' ? 2 * (k >> 1) : (k == 0 ? 0 : k == 1 ? 1 : k == 2 ? 1 : 2);
+    int dx = mode == 's' ? (k & 1) : mode == 'd' ? 2 * (k & 1) : (k == 0 ? 0 : k == 1 ? 1 : k == 2 ? 2 : 1);
+    for (int i = 0; i < r; ++i) { int t = dy; dy = dx; dx = -t; }
+    return want_dy ? dy : dx;
+}
+
+// the four rotations of one mode on the sample's 5x5 neighbourhood nb[(dy+2)*5 + (dx+2)] (register-resident: every
+// index is a compile-time constant), any interval, vertex rows gathered from the reference-layout table
+template <char MODE, int UP>
+__device__ __forceinline__ void generic_mode(const uint32_t (&nb)[25], const int8_t *__restrict__ lut, int interval,
+                                             const uint32_t (&stride)[4], int (&acc)[UP * UP])
+{
+    constexpr int UP2 = UP * UP;
+    constexpr uint32_t SBITS = 22, SMASK = (1u << SBITS) - 1u;   // L^3 <= 129^3 < 2^22
+    const int q = 1 << interval;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        uint32_t key[4];
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t t = nb[(k0_tap_off(MODE, r, k, true) + 2) * 5 + k0_tap_off(MODE, r, k, false) + 2];
+            v += (t >> interval) * stride[k];
+            key[k] = ((t & (uint32_t)(q - 1)) << SBITS) | stride[k];
+        }
+        sort4_desc(key[0], key[1], key[2], key[3]);
+        const int f1 = key[0] >> SBITS, f2 = key[1] >> SBITS, f3 = key[2] >> SBITS, f4 = key[3] >> SBITS;
+        const int w[5] = {q - f1, f1 - f2, f2 - f3, f3 - f4, f4};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            int vals[UP2];
+            load_row<UP>(lut + (size_t)v * UP2, vals);
+#pragma unroll
+            for (int j = 0; j < UP2; ++j) acc[subpixel_perm<UP>(r, j)] += w[k] * vals[j];
+            if (k < 4) v += key[k] & SMASK;
+        }
+    }
+}
+
 // one sample i = ((n*H + y)*W + x)*C + c through all modes x rotations + epilogue
 template <int UP>
 __device__ __forceinline__ void generic_sample(const StageArgs &a, size_t i)
@@ -40,7 +82,6 @@ __device__ __forceinline__ void generic_sample(const StageArgs &a, size_t i)
     const int q = 1 << a.interval;
     const int L = (1 << (8 - a.interval)) + 1;
     const uint32_t stride[4] = {(uint32_t)(L * L * L), (uint32_t)(L * L), (uint32_t)L, 1u};
-    constexpr uint32_t SBITS = 22, SMASK = (1u << SBITS) - 1u;   // L^3 <= 129^3 < 2^22
 
     const int xb = (int)(i % WC);
     const size_t row = i / WC;
@@ -49,35 +90,34 @@ __device__ __forceinline__ void generic_sample(const StageArgs &a, size_t i)
     const int x = xb / a.C, c = xb - x * a.C;
     const uint8_t *__restrict__ img = a.in + (size_t)n * a.H * WC;
 
+    // the 5x5 neighbourhood with replicate padding (sr/4_test_lut.py:293-296: np.pad(..., mode='edge') of the
+    // rotated image = clamped coordinates of the un-rotated one): 10 clamps and 25 loads per sample instead of
+    // 96 clamps, 48 loads and 96 run-time tap-table reads
+    uint32_t nb[25];
+    {
+        size_t yo[5];
+        int xo[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+            yo[d] = (size_t)clampi(y + d - 2, 0, a.H - 1) * WC;
+            xo[d] = clampi(x + d - 2, 0, a.W - 1) * a.C + c;
+        }
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) nb[dy * 5 + dx] = img[yo[dy] + xo[dx]];
+    }
+
     int acc[UP2];
 #pragma unroll
     for (int j = 0; j < UP2; ++j) acc[j] = 0;
 
     for (int m = 0; m < a.n_modes; ++m) {
         const int8_t *__restrict__ lut = a.lut[m];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            uint32_t key[4];
-            uint32_t v = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int yy = clampi(y + a.taps.dy[m][r][k], 0, a.H - 1);
-                const int xx = clampi(x + a.taps.dx[m][r][k], 0, a.W - 1);
-                const uint32_t t = img[(size_t)yy * WC + xx * a.C + c];
-                v += (t >> a.interval) * stride[k];
-                key[k] = ((t & (uint32_t)(q - 1)) << SBITS) | stride[k];
-            }
-            sort4_desc(key[0], key[1], key[2], key[3]);
-            const int f1 = key[0] >> SBITS, f2 = key[1] >> SBITS, f3 = key[2] >> SBITS, f4 = key[3] >> SBITS;
-            const int w[5] = {q - f1, f1 - f2, f2 - f3, f3 - f4, f4};
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                int vals[UP2];
-                load_row<UP>(lut + (size_t)v * UP2, vals);
-#pragma unroll
-                for (int j = 0; j < UP2; ++j) acc[subpixel_perm<UP>(r, j)] += w[k] * vals[j];
-                if (k < 4) v += key[k] & SMASK;
-            }
+        switch (a.modes[m]) {                      // validated at mulut_create: only s, d, y exist
+        case 's': generic_mode<'s', UP>(nb, lut, a.interval, stride, acc); break;
+        case 'd': generic_mode<'d', UP>(nb, lut, a.interval, stride, acc); break;
+        default: generic_mode<'y', UP>(nb, lut, a.interval, stride, acc); break;
         }
     }
 
