@@ -243,6 +243,46 @@ def numpy_reference_throughput(cfg, max_workers=0):
             "c_oracle_agrees_on_this_frame": same}
 
 
+def reference_module_step(luts, batch, crop, dev, steps=3):
+    """finetune.reference_module: the reference's own training step (3_finetune_lut.py:129-136) with its own
+    UNMODIFIED model.MuLUT (oracle/_ref/sr/model.py) on `dev` through ATen - the bar K4 is measured against."""
+    import tempfile
+    import torch
+    import torch.nn.functional as F
+    from oracle import ref_import as R
+    if not R.available():
+        return {"unavailable": "oracle/_ref not staged (python -m oracle.fetch_ref in the build container)"}
+    model = R.model_module()
+    with tempfile.TemporaryDirectory() as tmp:
+        for k, v in luts.items():
+            np.save(os.path.join(tmp, "LUT_x4_4bit_int8_{}.npy".format(k)), v)
+        net = model.MuLUT(lut_folder=tmp, stages=2, modes=["s", "d", "y"], upscale=4, interval=4).to(dev)
+    opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    from mulut_b200.cli.finetune_lut import synthetic_batch
+    im, lb = synthetic_batch(batch, crop, 4, 1000, dev)
+
+    def step():
+        opt.zero_grad()
+        loss = F.mse_loss(net(im), lb)
+        loss.backward()
+        opt.step()
+        return loss
+
+    loss0 = float(step().item())                       # warm-up (allocator, cuDNN-free: plain ATen indexing kernels)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    wall = (time.perf_counter() - t0) / steps * 1e3
+    return {"ms_per_step": e0.elapsed_time(e1) / steps, "wall_ms_per_step": wall, "batch": batch, "steps": steps,
+            "first_loss": loss0, "module": "unmodified reference model.MuLUT (sr/model.py) + torch.optim.Adam, eager ATen, "
+            "same GPU"}
+
+
 def run_reference_arm(args, rank, world):
     """--impl reference: the reference's CPU path.  The reference is pure Python
     and /root/reference does not exist on the GPU box, so this is the C port of
@@ -499,7 +539,8 @@ def main():
         from tools.finetune_bench import finetune_block
         try:
             finetune, ft_state = finetune_block(rank, world, local, dist if world > 1 else None, steps=args.finetune_steps,
-                                                warmup=10, clock_sampler=lambda: ClockSampler(local))
+                                                warmup=10, reference_fn=reference_module_step,
+                                                clock_sampler=lambda: ClockSampler(local))
             del ft_state                       # the captured graphs hold NCCL work: dropped before the group goes away
         except Exception as e:
             finetune = {"error": repr(e)[:400]}

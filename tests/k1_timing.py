@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel CUDA-event times of one config's step (device-resident), for A/B runs of side builds:
 
-    [MULUT_B200_LIB=mulut_b200/libmulut_b200_exp.so] python tools/k1_timing.py [--config cfg2] [--steps 10] [--check]
+    [MULUT_B200_LIB=mulut_b200/libmulut_b200_exp.so] python tests/k1_timing.py [--config cfg2] [--steps 10] [--check]
 """
 import argparse
 import os

@@ -56,6 +56,18 @@ def test_product_never_imports_oracle():
                 assert "oracle" not in src.replace("# oracle-free", ""), os.path.join(dp, f)
 
 
+def test_tools_never_import_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's baseline / parity legs may execute the oracle tree:
+    the helper scripts under tools/ must not (those that need a checker live under tests/)."""
+    import re
+    tools = os.path.join(ROOT, "tools")
+    for dp, _, files in os.walk(tools):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dp, f)
+
+
 def test_lut_naming_rules(gold_dir):
     from mulut_b200.infer import load_luts, lut_path
     # test path: 8 - interval (4_test_lut.py:331-332)

@@ -19,7 +19,6 @@ import argparse
 import json
 import os
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -72,46 +71,10 @@ def _time_graph(g, steps, warmup, world, dist, dev):
     return float(t.item())
 
 
-def reference_module_step(luts, batch, crop, dev, steps=3):
-    """The reference's own training step (3_finetune_lut.py:129-136) with its own model.MuLUT on `dev`."""
-    import torch
-    import torch.nn.functional as F
-    from oracle import ref_import as R
-    if not R.available():
-        return {"unavailable": "oracle/_ref not staged (python -m oracle.fetch_ref in the build container)"}
-    model = R.model_module()
-    with tempfile.TemporaryDirectory() as tmp:
-        for k, v in luts.items():
-            np.save(os.path.join(tmp, "LUT_x4_4bit_int8_{}.npy".format(k)), v)
-        net = model.MuLUT(lut_folder=tmp, stages=2, modes=["s", "d", "y"], upscale=4, interval=4).to(dev)
-    opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
-    from mulut_b200.cli.finetune_lut import synthetic_batch
-    im, lb = synthetic_batch(batch, crop, 4, 1000, dev)
-
-    def step():
-        opt.zero_grad()
-        loss = F.mse_loss(net(im), lb)
-        loss.backward()
-        opt.step()
-        return loss
-
-    loss0 = float(step().item())                       # warm-up (allocator, cuDNN-free: plain ATen indexing kernels)
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    wall = (time.perf_counter() - t0) / steps * 1e3
-    return {"ms_per_step": e0.elapsed_time(e1) / steps, "wall_ms_per_step": wall, "batch": batch, "steps": steps,
-            "first_loss": loss0, "module": "unmodified reference model.MuLUT (sr/model.py) + torch.optim.Adam, eager ATen, "
-            "same GPU"}
-
-
 def finetune_block(rank, world, local, dist=None, steps=30, warmup=10, batch=256, crop=48, smooth=False,
-                   reference=True, clock_sampler=None):
+                   reference_fn=None, clock_sampler=None):
+    """reference_fn(luts, batch, crop, dev, steps) -> dict: the reference-module leg (bench.py owns it: it runs code
+    staged under oracle/_ref, and only bench.py's baseline legs may execute the oracle tree)."""
     import torch
     import torch.nn.functional as F
     from mulut_b200.cli.finetune_lut import GraphedStep, synthetic_batch
@@ -194,9 +157,9 @@ def finetune_block(rank, world, local, dist=None, steps=30, warmup=10, batch=256
         "loss": loss, "clocks": clocks,
     }
     del graphs
-    if reference and world == 1 and rank == 0:
+    if reference_fn is not None and world == 1 and rank == 0:
         try:
-            ref = {"B{}".format(b): reference_module_step(luts, b, crop, dev, steps=3) for b in (32, batch)}
+            ref = {"B{}".format(b): reference_fn(luts, b, crop, dev, 3) for b in (32, batch)}
             r = ref["B{}".format(batch)]
             if "ms_per_step" in r:
                 ref["speedup_at_B{}".format(batch)] = r["ms_per_step"] / ms_full
@@ -223,9 +186,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     sys.path.insert(0, ROOT)
-    from bench import ClockSampler
+    from bench import ClockSampler, reference_module_step
     res, gs = finetune_block(rank, world, local, dist, args.steps, args.warmup, args.batch, args.crop, args.smooth,
-                             not args.no_reference, lambda: ClockSampler(local))
+                             None if args.no_reference else reference_module_step, lambda: ClockSampler(local))
     if rank == 0:
         print(json.dumps(res), flush=True)
     del gs                                       # the captured graphs hold NCCL work: drop them before the group
