@@ -167,12 +167,12 @@ def finetune_steps(model_G: MuLUT, steps: int, batch: int, crop: int, seed: int,
     model_G.train()
     losses, pending = [], []
 
-    def flush(i):
+    def flush(i, show=True):
         if pending:
             vals = [float(v) for v in torch.stack(pending).cpu()]
             losses.extend(vals)
             pending.clear()
-            if display_step and rank == 0:
+            if show and display_step and rank == 0:
                 log("Iter:{:6d}, loss:{:.3e}".format(i, float(np.mean(vals))))
 
     def batch_of(i):
@@ -197,6 +197,8 @@ def finetune_steps(model_G: MuLUT, steps: int, batch: int, crop: int, seed: int,
             pending.append(gs(im, lb, lr0 * lam(i)))       # LambdaLR: lr of step i is lr0 * lambda(i)
             if display_step and (i + 1) % display_step == 0:
                 flush(i + 1)
+            elif len(pending) >= 1024:                      # never hold more than ~1k device scalars
+                flush(i + 1, show=False)
             if on_step is not None:
                 on_step(i + 1, gs.opt)
         flush(start_iter + steps)
@@ -219,6 +221,8 @@ def finetune_steps(model_G: MuLUT, steps: int, batch: int, crop: int, seed: int,
         pending.append(loss.detach())
         if display_step and (i + 1) % display_step == 0:
             flush(i + 1)
+        elif len(pending) >= 1024:
+            flush(i + 1, show=False)
         if on_step is not None:
             on_step(i + 1, None)
     flush(start_iter + steps)
