@@ -268,19 +268,24 @@ def reference_module_step(luts, batch, crop, dev, steps=3):
         opt.step()
         return loss
 
+    on_gpu = torch.device(dev).type == "cuda"
     loss0 = float(step().item())                       # warm-up (allocator, cuDNN-free: plain ATen indexing kernels)
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if on_gpu:
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    e0.record()
+    if on_gpu:
+        e0.record()
     for _ in range(steps):
         step()
-    e1.record()
-    torch.cuda.synchronize(dev)
+    if on_gpu:
+        e1.record()
+        torch.cuda.synchronize(dev)
     wall = (time.perf_counter() - t0) / steps * 1e3
-    return {"ms_per_step": e0.elapsed_time(e1) / steps, "wall_ms_per_step": wall, "batch": batch, "steps": steps,
-            "first_loss": loss0, "module": "unmodified reference model.MuLUT (sr/model.py) + torch.optim.Adam, eager ATen, "
-            "same GPU"}
+    return {"ms_per_step": e0.elapsed_time(e1) / steps if on_gpu else wall, "wall_ms_per_step": wall, "batch": batch,
+            "steps": steps, "first_loss": loss0,
+            "module": "unmodified reference model.MuLUT (sr/model.py) + torch.optim.Adam, eager ATen, " +
+                      ("same GPU" if on_gpu else "host CPU, {} torch threads".format(torch.get_num_threads()))}
 
 
 def run_reference_arm(args, rank, world):

@@ -163,6 +163,8 @@ def finetune_block(rank, world, local, dist=None, steps=30, warmup=10, batch=256
             r = ref["B{}".format(batch)]
             if "ms_per_step" in r:
                 ref["speedup_at_B{}".format(batch)] = r["ms_per_step"] / ms_full
+            # the same module on the host cores: a bounded sample, batch 16, one step
+            ref["cpu_B16"] = reference_fn(luts, 16, crop, torch.device("cpu"), 1)
             res["reference_module"] = ref
         except Exception as e:                                 # the bar is a report, never a reason to lose the line
             res["reference_module"] = {"error": repr(e)[:300]}
