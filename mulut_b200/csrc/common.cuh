@@ -115,4 +115,15 @@ __device__ __forceinline__ uint32_t rhe_div_clamp_u8_magic(int num, uint32_t den
     return min(qd, 255u);
 }
 
+// Non-last stage epilogue, 0 <= t <= 254 * den, den even (den = q * 4M): round-half-even(t / den) needs neither the
+// clamp at 0 nor the one at 255.  With u = t + den/2, q' = floor(u / den) is the half-up rounding; it is one too many
+// exactly on a tie (u % den == 0) whose q' is odd.  Checked exhaustively for M = 1..8 in tests/test_host_logic.py.
+__device__ __forceinline__ uint32_t rhe_div_nonneg_magic(uint32_t t, uint32_t den, uint32_t magic)
+{
+    const uint32_t u = t + (den >> 1);
+    const uint32_t qd = __umulhi(u, magic);
+    const uint32_t rm = u - qd * den;
+    return qd - ((rm == 0u) ? (qd & 1u) : 0u);
+}
+
 }  // namespace mulut

@@ -68,6 +68,20 @@ def test_tools_never_import_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dp, f)
 
 
+def test_nonlast_epilogue_without_clamps_is_round_half_even():
+    """The integer form K1b uses for non-last stages (common.cuh: rhe_div_nonneg_magic): u = t + den/2,
+    q' = mulhi(u, magic), minus one on an odd tie - against numpy's round-half-even, every t in [0, 254 den]."""
+    for M in range(1, 9):
+        D = 64 * M
+        t = np.arange(0, 254 * D + 1, dtype=np.int64)
+        magic = 0xFFFFFFFF // D + 1
+        u = t + D // 2
+        q = (u * magic) >> 32
+        r = u - q * D
+        res = q - ((r == 0) & (q & 1))
+        assert (res == np.round(t / D)).all() and res.max() <= 254, M
+
+
 def test_lut_naming_rules(gold_dir):
     from mulut_b200.infer import load_luts, lut_path
     # test path: 8 - interval (4_test_lut.py:331-332)
