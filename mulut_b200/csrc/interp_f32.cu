@@ -336,45 +336,40 @@ __device__ __forceinline__ void load_qrow(const int8_t *__restrict__ q, int row,
     }
 }
 
-// simplex of four tap VALUES (model.py:122-160 without the pad/rotate bookkeeping)
+// simplex of four tap VALUES (model.py:122-160 without the pad/rotate bookkeeping).  K4 only: its taps have been rounded
+// to the integer grid, so the split (floor_divide / python remainder), the sort and the weights are done in integers -
+// the same values the float path of K2/K3 computes, at a sixth of the instructions (the float form with its fmodf /
+// floorf / rank sort cost 555 instructions per interpolation: the forward kernels were bound by them).
+// Order: fractions descending, ties -> higher tap index first (what the reference's 24 strict-inequality cases resolve
+// to; it only matters for the input gradient): key = f << 24 | tap << 22 | stride, sorted descending.
 __device__ __forceinline__ void simplex_from_taps(const float (&t)[4], int interval, int n_rows, Simplex &s)
 {
-    const float q = (float)(1 << interval);
+    const int q = 1 << interval;
     const int L = (1 << (8 - interval)) + 1;
-    const int stride[4] = {L * L * L, L * L, L, 1};
-    float f[4];
+    const uint32_t stride[4] = {(uint32_t)(L * L * L), (uint32_t)(L * L), (uint32_t)L, 1u};
+    uint32_t key[4];
     int v0 = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        int m;
-        split_msb_lsb(t[k], q, m, f[k]);
-        v0 += m * stride[k];
+        const int ti = __float2int_rn(t[k]);
+        v0 += (ti >> interval) * (int)stride[k];                 // arithmetic shift = floor division (any sign)
+        key[k] = ((uint32_t)(ti & (q - 1)) << 24) | ((uint32_t)k << 22) | stride[k];
     }
-    sort_taps(f, s.order);
-    float fs[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        fs[p] = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (s.order[p] == k) fs[p] = f[k];
-    }
+    sort4_desc(key[0], key[1], key[2], key[3]);
     s.v[0] = v0;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-        int st = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (s.order[p] == k) st = stride[k];
-        s.v[p + 1] = s.v[p] + st;
+        s.order[p] = (int)((key[p] >> 22) & 3u);
+        s.v[p + 1] = s.v[p] + (int)(key[p] & 0x3FFFFFu);
     }
 #pragma unroll
     for (int p = 0; p < 5; ++p) s.v[p] = min(max(s.v[p], 0), n_rows - 1);   // memory safety only
-    s.w[0] = q - fs[0];
-    s.w[1] = fs[0] - fs[1];
-    s.w[2] = fs[1] - fs[2];
-    s.w[3] = fs[2] - fs[3];
-    s.w[4] = fs[3];
+    const int f1 = (int)(key[0] >> 24), f2 = (int)(key[1] >> 24), f3 = (int)(key[2] >> 24), f4 = (int)(key[3] >> 24);
+    s.w[0] = (float)(q - f1);
+    s.w[1] = (float)(f1 - f2);
+    s.w[2] = (float)(f2 - f3);
+    s.w[3] = (float)(f3 - f4);
+    s.w[4] = (float)f4;
 }
 
 template <int UP>
