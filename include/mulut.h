@@ -204,6 +204,20 @@ int mulut_adam_step_f32(float *d_param, const float *d_grad, float *d_exp_avg, f
                         float *d_step, void *stream);
 
 /*
+ * Loss head of the training step: `x / 255.0` (sr/model.py:312) followed by F.mse_loss(pred, label)
+ * (sr/3_finetune_lut.py:132) and their backward, one kernel per direction.
+ *   d_x      float32, n elements: the last stage's output (0..255), 16-byte aligned
+ *   d_label  float32, n elements in [0, 1]
+ *   scale    1/255
+ *   forward : *d_loss = mean((x * scale - label)^2);  d_work16 = 16 bytes of device scratch
+ *   backward: d_grad_x[i] = *d_grad_loss * 2 / n * scale * (x[i] * scale - label[i])   (overwritten)
+ */
+int mulut_mse_head_fwd_f32(const float *d_x, const float *d_label, size_t n, float scale, void *d_work16,
+                           float *d_loss, void *stream);
+int mulut_mse_head_bwd_f32(const float *d_x, const float *d_label, size_t n, float scale,
+                           const float *d_grad_loss, float *d_grad_x, void *stream);
+
+/*
  * On-device report metrics of eltr._worker, sr/4_test_lut.py:309-314: PSNR and SSIM on the BT.601
  * luma of two RGB uint8 frames, definitions of common/utils.py:42-101 (_rgb2ycbcr, PSNR with
  * shave_border, cal_ssim: 11x11 Gaussian window sigma 1.5, 'valid', float64).

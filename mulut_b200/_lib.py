@@ -63,6 +63,10 @@ SYMBOLS = {
                                        _c.c_void_p]),
     "mulut_adam_step_f32": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p,
                                        _c.c_float, _c.c_float, _c.c_float, _c.c_float, _c.c_void_p, _c.c_void_p]),
+    "mulut_mse_head_fwd_f32": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_float, _c.c_void_p, _c.c_void_p,
+                                          _c.c_void_p]),
+    "mulut_mse_head_bwd_f32": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_float, _c.c_void_p, _c.c_void_p,
+                                          _c.c_void_p]),
     "mulut_eval_psnr_ssim_y_u8": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
                                              _c.POINTER(_c.c_double), _c.c_void_p]),
     "mulut_plan_bins": (_c.c_int, [_c.POINTER(_c.c_ulonglong), _c.c_longlong, _c.c_int, _c.c_ulonglong, _c.c_int,

@@ -114,6 +114,8 @@ class GraphedStep:
         self.params = [p for p in model_G.parameters() if p.requires_grad]
         self.bucket = mdist.FlatGradBucket(self.params)
         self.opt = mdist.FusedAdam(self.bucket, lr0, betas=(0.9, 0.999), eps=1e-8, weight_decay=weight_decay)
+        if getattr(model_G, "fused", False):
+            model_G.accumulate_grads_into(True)      # K4's backward adds straight into the bucket's views
         self.im = torch.zeros(im_shape, device=device)
         self.lb = torch.zeros(lb_shape, device=device)
         saved = [p.detach().clone() for p in self.params]
@@ -134,7 +136,10 @@ class GraphedStep:
 
     def _body(self):
         self.bucket.zero_()
-        loss = F.mse_loss(self.model(self.im), self.lb)
+        # pred = model(im); loss = F.mse_loss(pred, lb)  (3_finetune_lut.py:130-132) - with K4 the `/ 255` and the loss
+        # are one kernel per direction (MuLUT.forward_loss)
+        loss = self.model.forward_loss(self.im, self.lb) if hasattr(self.model, "forward_loss") else \
+            F.mse_loss(self.model(self.im), self.lb)
         loss.backward()
         self.bucket.all_reduce_mean()
         self.opt.step()

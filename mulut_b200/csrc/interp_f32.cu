@@ -853,8 +853,92 @@ adam_step_kernel(float *__restrict__ p, const float *__restrict__ g, float *__re
         p[i] = pi - step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
     }
 }
+// ---------------------------------------------------------------------------
+// Loss head of the training step (sr/model.py:312 `x / 255.0` + sr/3_finetune_lut.py:132 F.mse_loss) in one pass per
+// direction: ATen runs six elementwise / reduction kernels over the 9.4 M outputs of a cfg-4 step for it (77 us).
+//   forward : loss = mean((x * scale - label)^2)                      (scale = 1/255)
+//   backward: grad_x = grad_loss * 2 / n * scale * (x * scale - label)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mse_head_fwd_kernel(const float *__restrict__ x, const float *__restrict__ label, size_t n, float scale,
+                    double *__restrict__ acc /* [0] sum, [1] ticket as bits */, float *__restrict__ loss)
+{
+    double part = 0.0;
+    const size_t n4 = n / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(x) + i), b = __ldg(reinterpret_cast<const float4 *>(label) + i);
+        const float d0 = a.x * scale - b.x, d1 = a.y * scale - b.y, d2 = a.z * scale - b.z, d3 = a.w * scale - b.w;
+        part += (double)(d0 * d0 + d1 * d1) + (double)(d2 * d2 + d3 * d3);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (size_t i = n4 * 4; i < n; ++i) { const float d = x[i] * scale - label[i]; part += (double)(d * d); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __shared__ double s_part[8];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_part[w];
+        atomicAdd(acc, t);
+        __threadfence();
+        unsigned long long *ticket = reinterpret_cast<unsigned long long *>(acc + 1);
+        if (atomicAdd(ticket, 1ull) == gridDim.x - 1) {             // last block: the mean
+            __threadfence();
+            *loss = (float)(*reinterpret_cast<volatile double *>(acc) / (double)n);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mse_head_bwd_kernel(const float *__restrict__ x, const float *__restrict__ label, size_t n, float scale,
+                    const float *__restrict__ grad_loss, float *__restrict__ grad_x)
+{
+    const float k = __ldg(grad_loss) * (2.0f / (float)n) * scale;
+    const size_t n4 = n / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(x) + i), b = __ldg(reinterpret_cast<const float4 *>(label) + i);
+        reinterpret_cast<float4 *>(grad_x)[i] = make_float4(k * (a.x * scale - b.x), k * (a.y * scale - b.y),
+                                                            k * (a.z * scale - b.z), k * (a.w * scale - b.w));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (size_t i = n4 * 4; i < n; ++i) grad_x[i] = k * (x[i] * scale - label[i]);
+}
+
 __global__ void adam_tick_kernel(float *d_step) { *d_step += 1.f; }
 }  // namespace mulut
+
+extern "C" int mulut_mse_head_fwd_f32(const float *d_x, const float *d_label, size_t n, float scale, void *d_work16,
+                                      float *d_loss, void *stream)
+{
+    if (!d_x || !d_label || !d_work16 || !d_loss || n == 0) { set_error("mse_head_fwd: bad argument"); return MULUT_E_BAD_ARG; }
+    if ((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_label)) & 15) {
+        set_error("mse_head_fwd: x and label must be 16-byte aligned");
+        return MULUT_E_BAD_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    MULUT_CUDA(cudaMemsetAsync(d_work16, 0, 16, st));
+    size_t blocks = (n / 4 + 255) / 256 + 1;
+    if (blocks > (size_t)sm_count() * 8) blocks = (size_t)sm_count() * 8;
+    mse_head_fwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_x, d_label, n, scale, static_cast<double *>(d_work16), d_loss);
+    MULUT_CUDA(cudaGetLastError());
+    return MULUT_OK;
+}
+
+extern "C" int mulut_mse_head_bwd_f32(const float *d_x, const float *d_label, size_t n, float scale,
+                                      const float *d_grad_loss, float *d_grad_x, void *stream)
+{
+    if (!d_x || !d_label || !d_grad_loss || !d_grad_x || n == 0) { set_error("mse_head_bwd: bad argument"); return MULUT_E_BAD_ARG; }
+    if ((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_label) | reinterpret_cast<uintptr_t>(d_grad_x)) & 15) {
+        set_error("mse_head_bwd: buffers must be 16-byte aligned");
+        return MULUT_E_BAD_ARG;
+    }
+    size_t blocks = (n / 4 + 255) / 256 + 1;
+    if (blocks > (size_t)sm_count() * 8) blocks = (size_t)sm_count() * 8;
+    mse_head_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_x, d_label, n, scale, d_grad_loss, d_grad_x);
+    MULUT_CUDA(cudaGetLastError());
+    return MULUT_OK;
+}
 
 extern "C" int mulut_adam_step_f32(float *d_param, const float *d_grad, float *d_exp_avg, float *d_exp_avg_sq, size_t n,
                                    const float *d_lr, float beta1, float beta2, float eps, float weight_decay,

@@ -61,24 +61,31 @@ class FlatGradBucket:
     all-reduce covers them (replaces nothing in the reference: its multi-GPU
     finetune is unimplemented, 3_finetune_lut.py:156-157)."""
 
+    ALIGN = 4                                # elements: every view starts on a 16-byte boundary (K4 scatters into the
+                                             # views with 16-byte vector reductions when it accumulates in place)
+
     def __init__(self, params: List[torch.nn.Parameter]):
         self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+        self.offsets = []
+        n = 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         ref = self.params[0]
         self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
 
     def zero_(self) -> None:
         self.flat.zero_()
         # re-attach in case an optimizer dropped the views (set_to_none=True)
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             if p.grad is None or p.grad.data_ptr() != self.flat[off:off + p.numel()].data_ptr():
                 p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+
+    def packed(self) -> torch.Tensor:
+        """The gradients concatenated WITHOUT the alignment padding (parameter order)."""
+        return torch.cat([self.flat[off:off + p.numel()] for p, off in zip(self.params, self.offsets)])
 
     def all_reduce_mean(self) -> None:
         if dist.is_initialized() and dist.get_world_size() > 1:
@@ -99,14 +106,12 @@ class FusedAdam:
         ref = bucket.flat
         if not ref.is_cuda:
             raise RuntimeError("FusedAdam needs CUDA parameters (no CPU fallback)")
-        self.flat_param = torch.empty_like(ref)
-        off = 0
+        self.flat_param = torch.zeros_like(ref)          # same layout as the gradient bucket (padding stays zero)
         with torch.no_grad():
-            for p in bucket.params:
+            for p, off in zip(bucket.params, bucket.offsets):
                 n = p.numel()
                 self.flat_param[off:off + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat_param[off:off + n].view_as(p)
-                off += n
         self.exp_avg = torch.zeros_like(ref)
         self.exp_avg_sq = torch.zeros_like(ref)
         self.lr = torch.tensor(float(lr), device=ref.device)

@@ -65,9 +65,13 @@ class _StageFunction(torch.autograd.Function):
     ONE kernel per direction (mulut_stage_fwd_f32 / mulut_stage_bwd_f32)."""
 
     @staticmethod
-    def forward(ctx, x, upscale, modes, avg, bias, interval, *weights):
+    def forward(ctx, x, upscale, modes, avg, bias, interval, grad_targets, *weights):
+        # grad_targets: None, or one fp32 buffer per weight (e.g. the views of a FlatGradBucket) that the backward
+        # kernel accumulates INTO directly - autograd then gets None for the weights, which saves the zero-filled
+        # temporaries and the six accumulation kernels of the usual `.grad += returned gradient` (40 us per step)
         if not (x.is_cuda and all(w.is_cuda for w in weights)):
             raise RuntimeError("mulut_b200 fused stage needs CUDA tensors (no CPU fallback)")
+        ctx.grad_targets = grad_targets
         xs = x.detach().contiguous().float()
         ws = [w.detach().contiguous().float() for w in weights]
         B, C, h, wd = xs.shape
@@ -93,7 +97,11 @@ class _StageFunction(torch.autograd.Function):
         B, C, h, wd = xs.shape
         g = grad_out.contiguous().float()
         gx = torch.zeros_like(xs) if ctx.needs_input_grad[0] else None
-        gws = [torch.zeros_like(w) if ctx.needs_input_grad[6 + i] else None for i, w in enumerate(ws)]
+        direct = ctx.grad_targets is not None
+        if direct:
+            gws = [t if ctx.needs_input_grad[7 + i] else None for i, t in enumerate(ctx.grad_targets)]
+        else:
+            gws = [torch.zeros_like(w) if ctx.needs_input_grad[7 + i] else None for i, w in enumerate(ws)]
         ptrs = (ctypes.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
         gptrs = (ctypes.c_void_p * len(ws))(*[(t.data_ptr() if t is not None else None) for t in gws])
         stream = ctypes.c_void_p(torch.cuda.current_stream(xs.device).cuda_stream)
@@ -102,10 +110,47 @@ class _StageFunction(torch.autograd.Function):
                                                       xs.data_ptr(), B, C, h, wd, avg, bias, g.data_ptr(),
                                                       mask.data_ptr(), qws.data_ptr(), gptrs,
                                                       gx.data_ptr() if gx is not None else None, stream))
-        return (gx, None, None, None, None, None) + tuple(gws)
+        return (gx, None, None, None, None, None, None) + (tuple(None for _ in gws) if direct else tuple(gws))
 
 
-def fused_stage(x, weights, upscale, modes, avg, bias, interval=4, check_inputs=False):
+class _MseHead(torch.autograd.Function):
+    """`F.mse_loss(x / 255.0, label)` (sr/model.py:312 + sr/3_finetune_lut.py:132) as one kernel per direction
+    (mulut_mse_head_fwd_f32 / _bwd_f32): ATen needs six kernels over the 9.4 M outputs of a cfg-4 step for it."""
+
+    @staticmethod
+    def forward(ctx, x, label):
+        if not (x.is_cuda and label.is_cuda):
+            raise RuntimeError("mulut_b200 loss head needs CUDA tensors (no CPU fallback)")
+        if x.shape != label.shape:
+            raise ValueError("prediction and label shapes differ")
+        xs, lb = x.detach().contiguous().float(), label.detach().contiguous().float()
+        loss = torch.empty((), dtype=torch.float32, device=xs.device)
+        work = torch.empty(16, dtype=torch.uint8, device=xs.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(xs.device).cuda_stream)
+        with torch.cuda.device(xs.device):
+            _lib.check(_lib.lib().mulut_mse_head_fwd_f32(xs.data_ptr(), lb.data_ptr(), xs.numel(), 1.0 / 255.0,
+                                                         work.data_ptr(), loss.data_ptr(), stream))
+        ctx.save_for_backward(xs, lb)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        xs, lb = ctx.saved_tensors
+        gl = grad_loss.detach().contiguous().float()
+        gx = torch.empty_like(xs)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(xs.device).cuda_stream)
+        with torch.cuda.device(xs.device):
+            _lib.check(_lib.lib().mulut_mse_head_bwd_f32(xs.data_ptr(), lb.data_ptr(), xs.numel(), 1.0 / 255.0,
+                                                         gl.data_ptr(), gx.data_ptr(), stream))
+        return gx, None
+
+
+def mse_head(x_stage, label):
+    """mean((x_stage / 255 - label)^2) with its gradient, fused (x_stage: the last stage's output, 0..255)."""
+    return _MseHead.apply(x_stage, label)
+
+
+def fused_stage(x, weights, upscale, modes, avg, bias, interval=4, check_inputs=False, grad_targets=None):
     """x' = round(clamp(sum-with-per-pass-rounding / avg + bias, 0, 255)) for one stage.
 
     PRECONDITION: `x` is integer-valued (0..255 as float32) - what MuLUT.forward feeds every stage
@@ -121,7 +166,11 @@ def fused_stage(x, weights, upscale, modes, avg, bias, interval=4, check_inputs=
     for m in modes:
         if m not in ("s", "d", "y"):
             raise ValueError("Mode {} not implemented.".format(m))
-    return _StageFunction.apply(x, int(upscale), modes, float(avg), float(bias), int(interval), *weights)
+    if grad_targets is not None:
+        for w, t in zip(weights, grad_targets):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == w.shape):
+                raise ValueError("grad_targets must be contiguous fp32 CUDA buffers shaped like the weights")
+    return _StageFunction.apply(x, int(upscale), modes, float(avg), float(bias), int(interval), grad_targets, *weights)
 
 
 def interp_torch_batch(weight, upscale, mode, img_in, bd, interval=4):
@@ -141,6 +190,7 @@ class MuLUT(nn.Module):
         # stage inputs (see fused_stage); check_inputs=True verifies that on every call (debug: it synchronises)
         self.fused = fused
         self.check_inputs = check_inputs
+        self._grad_targets = None            # see accumulate_grads_into()
         self.interval = interval
         self.upscale = upscale
         self.modes = modes
@@ -163,10 +213,27 @@ class MuLUT(nn.Module):
         """BPDA: round forward, identity backward (model.py:59-67)."""
         return input + (torch.round(input) - input).detach()
 
+    def accumulate_grads_into(self, enabled=True):
+        """Fused path only: let the K4 backward accumulate the LUT gradients straight into each parameter's existing
+        `.grad` buffer (e.g. the views of a `FlatGradBucket`) instead of returning them to autograd.  The `.grad`
+        tensors must exist, be contiguous fp32 and stay the same objects (zero them in place between steps).
+        Hooks on the parameters do not see these gradients - which is why this is opt-in."""
+        self._grad_targets = bool(enabled)
+
     def InterpTorchBatch(self, weight, upscale, mode, img_in, bd):
         return interp_torch_batch(weight, upscale, mode, img_in, bd, self.interval)
 
+    def forward_loss(self, x, label):
+        """`F.mse_loss(self.forward(x), label)` with the final `/ 255` and the loss fused into one kernel per direction
+        (the fused path's training step; same value and gradients up to fp32 summation order)."""
+        if not self.fused:
+            return F.mse_loss(self.forward(x), label)
+        return mse_head(self._stages(x), label)
+
     def forward(self, x):
+        return self._stages(x) / 255.0
+
+    def _stages(self, x):
         x = x * 255.0
         modes, stages = self.modes, self.stages
         for s in range(stages):
@@ -183,7 +250,10 @@ class MuLUT(nn.Module):
                     if mode not in ("s", "d", "y"):
                         raise ValueError("Mode {} not implemented.".format(mode))
                 weights = [getattr(self, "weight_s{}_{}".format(stage, mode)) for mode in modes]
-                x = fused_stage(x, weights, scale, modes, avg_factor, bias, self.interval, self.check_inputs)
+                targets = None
+                if self._grad_targets and torch.is_grad_enabled() and all(w.grad is not None for w in weights):
+                    targets = [w.grad for w in weights]
+                x = fused_stage(x, weights, scale, modes, avg_factor, bias, self.interval, self.check_inputs, targets)
                 continue
             for mode in modes:
                 pad = mode_pad_dict[mode]
@@ -193,7 +263,7 @@ class MuLUT(nn.Module):
                     pred = pred + torch.rot90(self.InterpTorchBatch(weight, scale, mode, xin, pad), (4 - r) % 4, [2, 3])
                     pred = self.round_func(pred)
             x = self.round_func(torch.clamp((pred / avg_factor) + bias, 0, 255))
-        return x / 255.0
+        return x
 
     # -- the on-disk format's writer (3_finetune_lut.py:162-169) -------------------
     def export_luts(self, exp_dir=None):

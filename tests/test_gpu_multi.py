@@ -54,7 +54,7 @@ def _worker(rank, world, port, backend, q):
     loss.backward()
     bucket.all_reduce_mean()
     torch.cuda.synchronize()
-    q.put((rank, (b, e), out, bucket.flat.cpu().numpy()))
+    q.put((rank, (b, e), out, bucket.packed().cpu().numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -92,7 +92,7 @@ def test_two_rank_inference_and_finetune_match_single_process():
     im = (rng.integers(0, 256, (4, 1, 12, 12)) / 255.0).astype(np.float32)
     lb = (rng.integers(0, 256, (4, 1, 48, 48)) / 255.0).astype(np.float32)
     F.mse_loss(net(torch.tensor(im).cuda()), torch.tensor(lb).cuda()).backward()
-    full = bucket.flat.cpu().numpy()
+    full = bucket.packed().cpu().numpy()
     assert np.allclose(res[0][3], res[1][3])
     # equal shards: mean of per-rank mean losses == global mean loss
     assert norm_max_err(res[0][3], full) < 1e-5

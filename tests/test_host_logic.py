@@ -153,8 +153,10 @@ def test_flat_grad_bucket_single_process():
     ps = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7))]
     b = FlatGradBucket(ps)
     (ps[0].sum() * 2 + (ps[1] * 3).sum()).backward()
-    assert b.flat.numel() == 22
-    assert torch.equal(b.flat[:15], torch.full((15,), 2.0)) and torch.equal(b.flat[15:], torch.full((7,), 3.0))
+    # every view starts on a 16-byte boundary (4 floats): 15 -> 16, 7 -> 8
+    assert b.flat.numel() == 24 and b.offsets == [0, 16]
+    assert torch.equal(b.flat[:15], torch.full((15,), 2.0)) and torch.equal(b.flat[16:23], torch.full((7,), 3.0))
+    assert float(b.flat[15]) == 0 and float(b.flat[23]) == 0
     b.zero_()
     assert float(b.flat.abs().sum()) == 0 and ps[0].grad.data_ptr() == b.flat.data_ptr()
 
@@ -182,7 +184,7 @@ def _dp_worker(rank, world, port, q):
     loss = ((x @ w[0][:4] ).pow(2).mean() + w[1].sum() * x.mean())
     loss.backward()
     bucket.all_reduce_mean()
-    q.put((rank, bucket.flat.clone().numpy(), (b, e)))
+    q.put((rank, bucket.packed().clone().numpy(), (b, e)))
     dist.destroy_process_group()
 
 

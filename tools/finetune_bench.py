@@ -107,11 +107,11 @@ def finetune_block(rank, world, local, dist=None, steps=30, warmup=10, batch=256
 
     def p_fwd():
         with torch.no_grad():
-            return F.mse_loss(gs.model(gs.im), gs.lb)
+            return gs.model.forward_loss(gs.im, gs.lb)
 
     def p_fwd_bwd():
         gs.bucket.zero_()
-        l = F.mse_loss(gs.model(gs.im), gs.lb)
+        l = gs.model.forward_loss(gs.im, gs.lb)
         l.backward()
         return l.detach()
 
