@@ -546,6 +546,7 @@ def main():
             finetune, ft_state = finetune_block(rank, world, local, dist if world > 1 else None, steps=args.finetune_steps,
                                                 warmup=10, reference_fn=reference_module_step,
                                                 clock_sampler=lambda: ClockSampler(local))
+            ft_state.close()
             del ft_state                       # the captured graphs hold NCCL work: dropped before the group goes away
         except Exception as e:
             finetune = {"error": repr(e)[:400]}

@@ -75,8 +75,27 @@ class FlatGradBucket:
         self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
         for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+        self._pending = []                   # (lo, hi, work) of the ranges begin_range() has in flight
+
+    def range_of(self, params) -> Tuple[int, int]:
+        """[lo, hi) of the flat buffer covering `params` - they must be consecutive bucket entries."""
+        idx = sorted(next(i for i, q in enumerate(self.params) if q is p) for p in params)
+        if idx != list(range(idx[0], idx[0] + len(idx))):
+            raise ValueError("range_of: parameters are not consecutive in the bucket")
+        last = idx[-1]
+        hi = self.offsets[last + 1] if last + 1 < len(self.offsets) else self.flat.numel()
+        return self.offsets[idx[0]], hi
+
+    def begin_range(self, lo: int, hi: int) -> None:
+        """Start the all-reduce of flat[lo:hi] NOW (its gradients are final) so it runs under the rest of the
+        backward pass; `all_reduce_mean` reduces whatever was not begun, waits and divides.  Every rank must
+        begin the same ranges in the same order."""
+        if dist.is_initialized() and dist.get_world_size() > 1 and hi > lo:
+            work = dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
+            self._pending.append((lo, hi, work))
 
     def zero_(self) -> None:
+        self._pending = []
         self.flat.zero_()
         # re-attach in case an optimizer dropped the views (set_to_none=True)
         for p, off in zip(self.params, self.offsets):
@@ -89,7 +108,14 @@ class FlatGradBucket:
 
     def all_reduce_mean(self) -> None:
         if dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            pos = 0
+            for lo, hi, _ in sorted(self._pending, key=lambda t: t[0]) + [(self.flat.numel(), 0, None)]:
+                if lo > pos:                                   # a gap nobody began: reduce it here
+                    dist.all_reduce(self.flat[pos:lo], op=dist.ReduceOp.SUM)
+                pos = max(pos, hi)
+            for _, _, work in self._pending:
+                work.wait()
+            self._pending = []
             self.flat.div_(dist.get_world_size())
 
 

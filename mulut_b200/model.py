@@ -191,6 +191,7 @@ class MuLUT(nn.Module):
         self.fused = fused
         self.check_inputs = check_inputs
         self._grad_targets = None            # see accumulate_grads_into()
+        self._stage_grads_cb = None          # see on_stage_grads()
         self.interval = interval
         self.upscale = upscale
         self.modes = modes
@@ -219,6 +220,16 @@ class MuLUT(nn.Module):
         tensors must exist, be contiguous fp32 and stay the same objects (zero them in place between steps).
         Hooks on the parameters do not see these gradients - which is why this is opt-in."""
         self._grad_targets = bool(enabled)
+
+    def on_stage_grads(self, callback):
+        """Fused path with `accumulate_grads_into`: call `callback(stage)` (1-based) during backward as soon as the LUT
+        gradients of `stage` are complete, i.e. right after that stage's K4 backward has been launched - a data-parallel
+        step starts the all-reduce of the last stage's tables (16 of the 17 MB) under the first stage's backward.
+        The first stage reports nothing (its gradients are complete when backward returns).  None removes it."""
+        self._stage_grads_cb = callback
+
+    def stage_parameters(self, stage):
+        return [getattr(self, "weight_s{}_{}".format(stage, mode)) for mode in self.modes]
 
     def InterpTorchBatch(self, weight, upscale, mode, img_in, bd):
         return interp_torch_batch(weight, upscale, mode, img_in, bd, self.interval)
@@ -253,6 +264,9 @@ class MuLUT(nn.Module):
                 targets = None
                 if self._grad_targets and torch.is_grad_enabled() and all(w.grad is not None for w in weights):
                     targets = [w.grad for w in weights]
+                    if self._stage_grads_cb is not None and x.requires_grad:
+                        # fires when the gradient of this stage's INPUT exists: the stage's backward kernel is launched
+                        x.register_hook(lambda g, st=stage, cb=self._stage_grads_cb: (cb(st), None)[1])
                 x = fused_stage(x, weights, scale, modes, avg_factor, bias, self.interval, self.check_inputs, targets)
                 continue
             for mode in modes:

@@ -54,7 +54,47 @@ def _worker(rank, world, port, backend, q):
     loss.backward()
     bucket.all_reduce_mean()
     torch.cuda.synchronize()
-    q.put((rank, (b, e), out, bucket.packed().cpu().numpy()))
+    plain = bucket.packed().cpu().numpy()
+    # ---- the same step the way GraphedStep runs it: fused loss head, K4 accumulating into the bucket, the last
+    # stage's tables reduced from the backward hook while stage 1 still runs ----
+    begun = []
+    ranges = {st: bucket.range_of(net.stage_parameters(st)) for st in (1, 2)}
+    net.accumulate_grads_into(True)
+    net.on_stage_grads(lambda st: (begun.append(st), bucket.begin_range(*ranges[st])))
+    bucket.zero_()
+    net.forward_loss(torch.tensor(im[pb:pe], device=dev), torch.tensor(lb[pb:pe], device=dev)).backward()
+    n_pending = len(bucket._pending)
+    bucket.all_reduce_mean()
+    torch.cuda.synchronize()
+    assert begun == [2] and n_pending == 1
+    assert norm_max_err(bucket.packed().cpu().numpy(), plain) < 1e-5
+    net.on_stage_grads(None)
+    net.accumulate_grads_into(False)
+    if backend == "nccl":
+        # and captured: two replays of the graph on the same batch equal two eager steps
+        from mulut_b200.cli.finetune_lut import GraphedStep
+        import copy
+        net2 = copy.deepcopy(net)
+        os.environ["MULUT_AR_OVERLAP"] = "1"
+        gs = GraphedStep(net2, (pe - pb, 1, 12, 12), (pe - pb, 1, 48, 48), 1e-3)
+        assert net2._stage_grads_cb is not None
+        ims, lbs = torch.tensor(im[pb:pe], device=dev), torch.tensor(lb[pb:pe], device=dev)
+        l0 = float(gs(ims, lbs, 1e-3).item())
+        gs(ims, lbs, 1e-3)
+        torch.cuda.synchronize()
+        os.environ["MULUT_AR_OVERLAP"] = "0"
+        net3 = copy.deepcopy(net)
+        gs3 = GraphedStep(net3, (pe - pb, 1, 12, 12), (pe - pb, 1, 48, 48), 1e-3)
+        assert net3._stage_grads_cb is None
+        l3 = float(gs3(ims, lbs, 1e-3).item())
+        gs3(ims, lbs, 1e-3)
+        torch.cuda.synchronize()
+        assert abs(l0 - l3) < 1e-6 * max(1.0, abs(l3))
+        for pa, pb_ in zip(net2.parameters(), net3.parameters()):
+            assert norm_max_err(pa.detach().cpu().numpy(), pb_.detach().cpu().numpy()) < 1e-5
+        gs.close(); gs3.close()
+        del gs, gs3, net2, net3
+    q.put((rank, (b, e), out, plain))
     dist.barrier()
     dist.destroy_process_group()
 

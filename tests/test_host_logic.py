@@ -183,7 +183,17 @@ def _dp_worker(rank, world, port, q):
     # per-rank MEAN loss over an equal share, like F.mse_loss on the rank's batch
     loss = ((x @ w[0][:4] ).pow(2).mean() + w[1].sum() * x.mean())
     loss.backward()
+    whole = bucket.flat.clone()
     bucket.all_reduce_mean()
+    reduced = bucket.flat.clone()
+    # the same reduction started range by range (what a step does under its backward pass): second table first,
+    # then the first one is the gap all_reduce_mean fills
+    bucket.flat.copy_(whole)
+    assert bucket.range_of([w[1]]) == (bucket.offsets[1], bucket.flat.numel())
+    assert bucket.range_of(w) == (0, bucket.flat.numel())
+    bucket.begin_range(*bucket.range_of([w[1]]))
+    bucket.all_reduce_mean()
+    assert torch.equal(bucket.flat, reduced) and not bucket._pending
     q.put((rank, bucket.packed().clone().numpy(), (b, e)))
     dist.destroy_process_group()
 

@@ -101,7 +101,10 @@ def finetune_block(rank, world, local, dist=None, steps=30, warmup=10, batch=256
     loss = float(gs.loss.item())
     clocks = sampler.stop() if sampler else None
 
-    # ---- the phases, each as its own graph (same buffers, same kernels) ----
+    # ---- the phases, each as its own graph (same buffers, same kernels); the step itself starts the all-reduce of
+    # the last stage's tables under the first stage's backward (GraphedStep), the phases are timed one after another ----
+    overlapped = gs.model._stage_grads_cb is not None
+    gs.model.on_stage_grads(None)
     def p_zero():
         gs.bucket.zero_()
 
@@ -151,7 +154,7 @@ def finetune_block(rank, world, local, dist=None, steps=30, warmup=10, batch=256
         "steps": steps, "warmup": warmup, "breakdown_ms": breakdown,
         "breakdown_how": "each phase captured as its own CUDA graph and replayed {} times between CUDA events; backward = "
                          "(zero+forward+backward) - zero_grad - forward_mse".format(steps),
-        "allreduce": ar, "allreduce_bytes": nbytes,
+        "allreduce": ar, "allreduce_bytes": nbytes, "allreduce_overlaps_backward": overlapped,
         "lut_grad_scatter_adds_per_step": n_adds, "scatter_adds_per_s": n_adds / (ms_full * 1e-3),
         "scatter_adds_per_s_backward_only": n_adds / (bwd * 1e-3) if bwd > 0 else None,
         "loss": loss, "clocks": clocks,
@@ -193,6 +196,7 @@ def main():
                              None if args.no_reference else reference_module_step, lambda: ClockSampler(local))
     if rank == 0:
         print(json.dumps(res), flush=True)
+    gs.close()
     del gs                                       # the captured graphs hold NCCL work: drop them before the group
     torch.cuda.synchronize()
     if world > 1:
