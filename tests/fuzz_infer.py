@@ -3,7 +3,8 @@
     python tests/fuzz_infer.py <first seed> <last seed> [scale=2]      # on the GPU box
 
 Random C in 1..4, TMA-mappable and arbitrary widths, 1-3 stages, mode subsets, five value distributions, orphaning on/off.
-Round 1: scale 2 seeds 0..699, scales 1, 3 and 4 seeds 0..119, both kernel selections: 0 mismatches."""
+Round 1: scale 2 seeds 0..699, scales 1, 3 and 4 seeds 0..119, both kernel selections: 0 mismatches.
+Round 2 (HEAD, after the K1b / K1f / K0 / K1e3 rewrites): scale 2 seeds 0..399, scales 1, 3 and 4 seeds 0..99: 0 mismatches."""
 import os, sys, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mulut_b200.infer import LutEngine

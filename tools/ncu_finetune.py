@@ -1,8 +1,13 @@
 #!/usr/bin/env python
-"""Three eager cfg4 finetune steps (K4 forward x1/x4, MSE, K4 backward x4/x1) for `ncu` captures:
+"""Three eager cfg4 finetune steps for `ncu` captures, launched the way `GraphedStep` launches them (zero the gradient
+bucket, K4 forward x1 / x4, fused loss head, K4 backward x4 / x1 accumulating into the bucket, fused Adam):
 
     ncu --set full --clock-control none --import-source on -k regex:'stage_(fwd|bwd)' -s 8 -c 4 \\
         -o gpurun_out/prof_k4 python tools/ncu_finetune.py [--smooth]
+    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_ft.csv \\
+        python tools/ncu_finetune.py                       # launch list: every kernel of the three steps
+
+`--unfused-head` keeps `F.mse_loss(net(im), lb)` and autograd's own accumulation (the step before the loss head).
 """
 import os
 import sys
@@ -25,10 +30,21 @@ def main():
         coarse = torch.randint(0, 256, (256, 1, 8, 8), generator=g).float()
         im = torch.round(F.interpolate(coarse, scale_factor=8, mode="bilinear", align_corners=False)[..., :48, :48]
                          .clamp(0, 255)).div(255.0).to(dev).contiguous()
-    for _ in range(3):
-        net.zero_grad(set_to_none=False)
-        loss = F.mse_loss(net(im), lb)
-        loss.backward()
+    if "--unfused-head" in sys.argv:
+        for _ in range(3):
+            net.zero_grad(set_to_none=False)
+            loss = F.mse_loss(net(im), lb)
+            loss.backward()
+    else:
+        from mulut_b200 import dist as mdist
+        bucket = mdist.FlatGradBucket(list(net.parameters()))
+        opt = mdist.FusedAdam(bucket, 1e-4)
+        net.accumulate_grads_into(True)
+        for _ in range(3):
+            bucket.zero_()
+            loss = net.forward_loss(im, lb)
+            loss.backward()
+            opt.step()
     torch.cuda.synchronize()
     print("ok", float(loss))
 
