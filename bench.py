@@ -548,6 +548,12 @@ def main():
                                                 clock_sampler=lambda: ClockSampler(local))
             ft_state.close()
             del ft_state                       # the captured graphs hold NCCL work: dropped before the group goes away
+            # the same step on natural-like (smooth) patches: the realistic case for the LUT-gradient scatter
+            smooth, ft_state = finetune_block(rank, world, local, dist if world > 1 else None, steps=args.finetune_steps,
+                                              warmup=10, smooth=True, phases_wanted=False)
+            ft_state.close()
+            del ft_state
+            finetune["smooth_patches"] = smooth
         except Exception as e:
             finetune = {"error": repr(e)[:400]}
         torch.cuda.synchronize()

@@ -173,7 +173,9 @@ int mulut_interp_bwd_f32(const float *d_weight, int n_rows, int up, char mode,
  *   d_mask     uint8, same shape: 1 where 0 <= pred/avg + bias <= 255 (clamp passes the gradient)
  *   d_workspace  mulut_stage_workspace_bytes() bytes, 16-byte aligned, caller-owned: the forward
  *              writes the quantised tables clamp(round(w*127), -127, 127) (model.py:74-76) there as
- *              int8 rows + clamp flags; hand the SAME buffer to the matching backward call.
+ *              int8 rows + clamp flags; hand the SAME buffer to the matching backward call (which also uses
+ *              its tail as scratch: copies of the gradient tables for inputs that put most updates on a few
+ *              hot LUT rows - one backward call per workspace at a time).
  */
 size_t mulut_stage_workspace_bytes(int n_modes, int n_rows, int up);
 int mulut_stage_fwd_f32(const float *const *d_weights, int n_modes, const char *modes, int n_rows,
@@ -185,6 +187,7 @@ int mulut_stage_fwd_f32(const float *const *d_weights, int n_modes, const char *
  * model.py:59-67): G_pred = grad_out * mask / avg feeds all 4*n_modes passes.
  *   d_grad_weights  n_modes tables float32 (n_rows, up^2), ACCUMULATED INTO; entries may be NULL
  *   d_grad_x        float32 (B, C, h, w), ACCUMULATED INTO; may be NULL
+ *   d_workspace     the forward call's buffer (const as far as the quantised tables go; see above)
  */
 int mulut_stage_bwd_f32(const float *const *d_weights, int n_modes, const char *modes, int n_rows,
                         int up, int interval, const float *d_x, int B, int C, int h, int w,

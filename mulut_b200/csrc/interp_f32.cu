@@ -279,6 +279,10 @@ struct StageF32Args {
     const int8_t *wq[MULUT_MAX_MODES];       // quantised once per call: clamp(rint(w*127), +-127), rows of q_pitch(up) bytes
     const uint16_t *wflag[MULUT_MAX_MODES];  // bit j: the clamp passes the gradient of column j (|rint(w*127)| <= 127)
     float *gweight[MULUT_MAX_MODES];         // backward only: accumulated into
+    float *replica;                          // backward only: (n_replicas - 1) x n_modes scratch tables, or null
+    size_t replica_stride;                   // floats per scratch table (n_rows * up^2 rounded up to 4)
+    int n_replicas;                          // 1 = every CTA adds into gweight directly
+    int merge;                               // hot rows: lanes of a warp on one row merge before the red (match.any tree)
     TapTable taps;
 };
 
@@ -290,6 +294,17 @@ __host__ __device__ constexpr int q_pitch(int up) { return up == 1 ? 1 : up == 2
 static size_t align16(size_t b) { return (b + 15) / 16 * 16; }
 static size_t stage_ws_mode_bytes(int n_rows, int up) { return align16((size_t)n_rows * q_pitch(up)) + align16((size_t)n_rows * 2); }
 constexpr size_t STAGE_WS_TAIL = 16;       // row-sharing statistics of the forward pass (see StageF32Args::stats)
+// Gradient replicas (backward, hot rows): on natural / smooth patches a few hundred LUT rows take most of the updates and
+// the L2 serialises atomics on one address - the same 141 M vector reds that take 0.82 ms on noise took 2.07 ms (1.56 ms
+// with the warp merge).  When the forward's row-sharing statistic says so, CTA b adds into table copy b % K4_REPLICAS
+// (copy 0 is the caller's gradient buffer, the others live in the workspace, zeroed before and summed into copy 0 after
+// the kernel): a quarter of the collisions per address, spread over four times as many L2 slices.
+constexpr int K4_REPLICAS = 4;
+static size_t replica_table_floats(int n_rows, int up) { return ((size_t)n_rows * up * up + 3) / 4 * 4; }
+static size_t stage_ws_replica_bytes(int n_modes, int n_rows, int up)
+{
+    return (size_t)(K4_REPLICAS - 1) * n_modes * replica_table_floats(n_rows, up) * sizeof(float);
+}
 
 template <int UP>
 __global__ void __launch_bounds__(256)
@@ -486,7 +501,8 @@ constexpr int K4_P = K4_T + 4;           // + 2-pixel halo on every side
 
 template <int UP, bool AGG>
 __device__ __forceinline__ void stage_bwd_body(const StageF32Args &a, const float *__restrict__ gout,
-                                               const uint8_t *__restrict__ mask, float *__restrict__ gx, float *s_gx)
+                                               const uint8_t *__restrict__ mask, float *__restrict__ gx, float *s_gx,
+                                               int rep)
 {
     constexpr int UP2 = UP * UP;
     const int tiles_x = (a.w + K4_T - 1) / K4_T, tiles_y = (a.h + K4_T - 1) / K4_T;
@@ -518,6 +534,7 @@ __device__ __forceinline__ void stage_bwd_body(const StageF32Args &a, const floa
             const int8_t *__restrict__ Q = a.wq[m];
             const uint16_t *__restrict__ FL = a.wflag[m];
             float *__restrict__ GW = a.gweight[m];
+            if (GW && rep) GW = a.replica + ((size_t)(rep - 1) * a.n_modes + m) * a.replica_stride;   // hot rows: this CTA's copy
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 float t[4];
@@ -596,9 +613,175 @@ stage_bwd_kernel(const __grid_constant__ StageF32Args a, const float *__restrict
 {
     __shared__ float s_gx[K4_P * K4_P];
     // aggregate when more than a quarter of the forward's lanes shared a LUT row with a neighbour
-    const bool agg = a.aggregate == 2 ? (4ull * a.stats[0] > (unsigned long long)a.stats[1]) : a.aggregate != 0;
-    if (agg) stage_bwd_body<UP, true>(a, gout, mask, gx, s_gx);
-    else stage_bwd_body<UP, false>(a, gout, mask, gx, s_gx);
+    const bool hot = a.aggregate == 2 ? (4ull * a.stats[0] > (unsigned long long)a.stats[1]) : a.aggregate != 0;
+    const int rep = (hot && a.n_replicas > 1) ? (int)(blockIdx.x % a.n_replicas) : 0;
+    if (hot && a.merge) stage_bwd_body<UP, true>(a, gout, mask, gx, s_gx, rep);
+    else stage_bwd_body<UP, false>(a, gout, mask, gx, s_gx, rep);
+}
+
+// ---------------------------------------------------------------------------
+// K4p: the x1 stage's LUT gradients accumulated in SHARED MEMORY ("private" backward).
+// stage_bwd_kernel<1> issues 60 scalar red.global.add per pixel and runs at the L2's atomic rate
+// (131 G ops/s, lts 75 %).  A x1 table at interval 4 is 83 521 floats; the rows one pixel touches lie in the
+// slabs a in {m_a, m_a + 1} of its centre tap, so the pixels with a centre value < 128 only touch slabs 0..8 and
+// the others slabs 8..16: 9 x 4913 floats = 177 KB, one SM's shared memory.  A persistent CTA serves ONE
+// (mode, half): its warps scan their share of the pixels, queue the ones of their half whose output gradient is
+// live (per-warp ring in shared memory, so the 32 lanes always work on 32 queued pixels), add the 4 x 5 vertex
+// contributions with shared-memory atomics (a CAS loop for fp32: the merge tree of the global kernel runs first
+// when the forward saw lanes sharing rows) and the CTA flushes its slab range once with 16-byte vector reds:
+// 6.5 M floats per launch instead of 35 M scalar reds.  Used when the stage needs no input gradient (stage 1)
+// and there are enough pixels to pay for the flush (see use_private_bwd).  stage_bwd_kernel<1> 269 -> 147 us at batch
+// 256 on noise patches, 450 -> 278 us on smooth ones.
+// ---------------------------------------------------------------------------
+constexpr int K4P_SLAB = 17 * 17 * 17;           // rows per value of tap a at interval 4
+constexpr int K4P_ROWS = 9 * K4P_SLAB;           // one half: slabs 0..8 or 8..16
+constexpr int K4P_THREADS = 768;
+constexpr int K4P_WARPS = K4P_THREADS / 32;
+constexpr int K4P_RING = 64;                     // per-warp queue of pixel indices (< 32 left + 32 appended)
+constexpr size_t K4P_SMEM = (size_t)(K4P_ROWS + 3) / 4 * 16 + (size_t)K4P_WARPS * K4P_RING * 4;
+
+template <bool AGG>
+__device__ __forceinline__ void private_bwd_pixel(const StageF32Args &a, int m, int half_base, size_t p, float g,
+                                                  unsigned active, float *__restrict__ s_tab)
+{
+    const int x = (int)(p % a.w);
+    const size_t rr = p / a.w;
+    const int y = (int)(rr % a.h);
+    const float *__restrict__ plane = a.x + (rr / a.h) * (size_t)a.h * a.w;
+    const uint16_t *__restrict__ FL = a.wflag[m];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int yy = clampi(y + a.taps.dy[m][r][k], 0, a.h - 1);
+            const int xx = clampi(x + a.taps.dx[m][r][k], 0, a.w - 1);
+            t[k] = rintf(__ldg(plane + (size_t)yy * a.w + xx));
+        }
+        Simplex s;
+        simplex_from_taps(t, 4, a.n_rows, s);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            float c[1];
+            c[0] = (__ldg(FL + s.v[k]) & 1u) ? 127.f * (s.w[k] * g) : 0.f;     // same product as stage_bwd_body
+            const int rel = min(max(s.v[k] - half_base, 0), K4P_ROWS - 1);      // in range for inputs 0..255
+            bool live = s.w[k] != 0.f;
+            if (AGG) live = warp_merge_rows<1>(active, live ? rel : -1 - (int)(threadIdx.x & 31), c) && live;
+            if (live && c[0] != 0.f) atomicAdd(s_tab + rel, c[0]);
+        }
+    }
+}
+
+template <bool AGG>
+__device__ __forceinline__ void private_bwd_body(const StageF32Args &a, const float *__restrict__ gout,
+                                                 const uint8_t *__restrict__ mask, float *s_tab, uint32_t *s_ring)
+{
+    const int kinds = 2 * a.n_modes;
+    const int kind = blockIdx.x % kinds, slot = blockIdx.x / kinds;
+    const int nslots = ((int)gridDim.x - kind + kinds - 1) / kinds;
+    const int m = kind >> 1, half = kind & 1;
+    const int half_base = half ? 8 * K4P_SLAB : 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t total = (size_t)a.BC * a.h * a.w;
+    const float inv_q = 1.f / 16.f;
+    for (int i = threadIdx.x; i < (K4P_ROWS + 3) / 4 * 4; i += blockDim.x) s_tab[i] = 0.f;
+    __syncthreads();
+
+    uint32_t *ring = s_ring + warp * K4P_RING;
+    int head = 0, qn = 0;                                      // warp-uniform
+    const size_t stride = (size_t)nslots * K4P_WARPS * 32;
+    for (size_t base = ((size_t)slot * K4P_WARPS + warp) * 32; base < total; base += stride) {
+        const size_t p = base + lane;
+        bool mine = false;
+        if (p < total && mask[p]) {
+            const int ta = __float2int_rn(__ldg(a.x + p));
+            mine = ((ta >= 128) == (half != 0)) && __ldg(gout + p) != 0.f;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, mine);
+        // (pixel indices as 32 bits: the launcher only takes this path below 2^32 pixels)
+        if (mine) ring[(head + qn + __popc(b & ((1u << lane) - 1u))) & (K4P_RING - 1)] = (uint32_t)p;
+        qn += __popc(b);
+        __syncwarp();
+        if (qn >= 32) {
+            const size_t pp = ring[(head + lane) & (K4P_RING - 1)];
+            const float g = __fdiv_rn(__ldg(gout + pp), a.avg) * inv_q;
+            private_bwd_pixel<AGG>(a, m, half_base, pp, g, 0xffffffffu, s_tab);
+            head = (head + 32) & (K4P_RING - 1);
+            qn -= 32;
+            __syncwarp();
+        }
+    }
+    {
+        const unsigned active = __ballot_sync(0xffffffffu, lane < qn);
+        if (lane < qn) {
+            const size_t pp = ring[(head + lane) & (K4P_RING - 1)];
+            const float g = __fdiv_rn(__ldg(gout + pp), a.avg) * inv_q;
+            private_bwd_pixel<AGG>(a, m, half_base, pp, g, active, s_tab);
+        }
+    }
+    __syncthreads();
+    float *__restrict__ gw = a.gweight[m] + half_base;
+    const float4 *s4 = reinterpret_cast<const float4 *>(s_tab);
+    for (int i = threadIdx.x; i < K4P_ROWS / 4; i += blockDim.x) {
+        const float4 v = s4[i];
+        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_v4(gw + 4 * i, v.x, v.y, v.z, v.w);
+    }
+    if (threadIdx.x < K4P_ROWS % 4) {
+        const int i = K4P_ROWS / 4 * 4 + threadIdx.x;
+        if (s_tab[i] != 0.f) atomicAdd(gw + i, s_tab[i]);
+    }
+}
+
+__global__ void __launch_bounds__(K4P_THREADS, 1)
+stage1_bwd_private_kernel(const __grid_constant__ StageF32Args a, const float *__restrict__ gout,
+                          const uint8_t *__restrict__ mask)
+{
+    extern __shared__ __align__(16) unsigned char k4p_smem[];
+    float *s_tab = reinterpret_cast<float *>(k4p_smem);
+    uint32_t *s_ring = reinterpret_cast<uint32_t *>(k4p_smem + (size_t)(K4P_ROWS + 3) / 4 * 16);
+    // no warp merge here: lanes on one row retry their shared-memory CAS a few times, which costs less than the
+    // match + shuffle tree (smooth patches: 278 us without, 477 us with; noise: 147 us)
+    private_bwd_body<false>(a, gout, mask, s_tab, s_ring);
+}
+
+__device__ __forceinline__ bool stage_rows_are_hot(const StageF32Args &a)
+{
+    return a.aggregate == 2 ? (4ull * a.stats[0] > (unsigned long long)a.stats[1]) : a.aggregate != 0;
+}
+
+// Both run on the stage's stream around stage_bwd_kernel and return at once when the replicas are not in use.
+__global__ void __launch_bounds__(256) replica_zero_kernel(const __grid_constant__ StageF32Args a)
+{
+    if (!stage_rows_are_hot(a)) return;
+    const size_t n4 = (size_t)(a.n_replicas - 1) * a.n_modes * a.replica_stride / 4;
+    float4 *__restrict__ r4 = reinterpret_cast<float4 *>(a.replica);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+        r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(256) replica_sum_kernel(const __grid_constant__ StageF32Args a, int up2)
+{
+    if (!stage_rows_are_hot(a)) return;
+    const size_t n = (size_t)a.n_rows * up2;
+    for (int m = 0; m < a.n_modes; ++m) {
+        float *__restrict__ gw = a.gweight[m];
+        if (!gw) continue;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+            float acc = 0.f;
+            for (int r = 1; r < a.n_replicas; ++r) acc += a.replica[((size_t)(r - 1) * a.n_modes + m) * a.replica_stride + i];
+            if (acc != 0.f) gw[i] += acc;
+        }
+    }
+}
+
+// MULUT_K4_PRIVATE: 0 never, 1 whenever the stage qualifies, default: when it has >= 2^16 pixels.  Measured on 48 x 48
+// patches, whole step: batch 256 1.42 -> 1.29 ms, 128 0.78 -> 0.72, 64 0.51 -> 0.48, 32 (73 728 pixels) 0.27 -> 0.26;
+// the fixed cost (zeroing and flushing 148 x 177 KB) is not measured below that, so smaller launches keep the reds.
+static bool use_private_bwd(size_t total)
+{
+    const char *e = getenv("MULUT_K4_PRIVATE");
+    if (e) return atoi(e) != 0;
+    return total >= ((size_t)1 << 16);
 }
 
 static int fill_stage_args(StageF32Args &a, const float *const *weights, int n_modes, const char *modes, int n_rows,
@@ -634,6 +817,10 @@ static int fill_stage_args(StageF32Args &a, const float *const *weights, int n_m
         a.wflag[m] = reinterpret_cast<const uint16_t *>(base + align16((size_t)n_rows * q_pitch(up)));
     }
     a.stats = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(workspace) + (size_t)n_modes * stage_ws_mode_bytes(n_rows, up));
+    a.replica = reinterpret_cast<float *>(static_cast<uint8_t *>(workspace) + (size_t)n_modes * stage_ws_mode_bytes(n_rows, up) +
+                                          STAGE_WS_TAIL);
+    a.replica_stride = replica_table_floats(n_rows, up);
+    a.n_replicas = 1;
     a.x = x; a.BC = B * C; a.h = h; a.w = w; a.n_modes = n_modes; a.interval = interval; a.n_rows = n_rows;
     a.avg = avg; a.bias = bias;
     return MULUT_OK;
@@ -755,7 +942,7 @@ extern "C" int mulut_interp_pass_f64(const float *d_weight, int n_rows, const fl
 extern "C" size_t mulut_stage_workspace_bytes(int n_modes, int n_rows, int up)
 {
     if (n_modes < 1 || n_rows < 1 || up < 1 || up > 4) return 0;
-    return (size_t)n_modes * stage_ws_mode_bytes(n_rows, up) + STAGE_WS_TAIL;
+    return (size_t)n_modes * stage_ws_mode_bytes(n_rows, up) + STAGE_WS_TAIL + stage_ws_replica_bytes(n_modes, n_rows, up);
 }
 
 extern "C" int mulut_stage_fwd_f32(const float *const *d_weights, int n_modes, const char *modes, int n_rows, int up,
@@ -816,6 +1003,32 @@ extern "C" int mulut_stage_bwd_f32(const float *const *d_weights, int n_modes, c
     const size_t blocks = (size_t)B * C * ((h + K4_T - 1) / K4_T) * ((w + K4_T - 1) / K4_T);
     if (blocks > 0x7fffffffull) { set_error("stage_bwd: too many tiles"); return MULUT_E_BAD_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
+    if (up == 1 && !d_grad_x && interval == 4 && total < 0xffffffffull && use_private_bwd(total)) {
+        bool ok = sm_count() >= 2 * n_modes;
+        for (int m = 0; m < n_modes; ++m) ok &= a.gweight[m] != nullptr && !(reinterpret_cast<uintptr_t>(a.gweight[m]) & 15);
+        if (ok) {
+            static bool attr_set[64] = {false};
+            int dev = 0;
+            MULUT_CUDA(cudaGetDevice(&dev));
+            if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+                MULUT_CUDA(cudaFuncSetAttribute(stage1_bwd_private_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)K4P_SMEM));
+                attr_set[dev] = true;
+            }
+            stage1_bwd_private_kernel<<<(unsigned)sm_count(), K4P_THREADS, K4P_SMEM, st>>>(a, d_grad_out, d_mask);
+            MULUT_CUDA(cudaGetLastError());
+            return MULUT_OK;
+        }
+    }
+    bool any_gw = false;
+    for (int m = 0; m < n_modes; ++m) any_gw |= a.gweight[m] != nullptr;
+    { const char *e = getenv("MULUT_K4_REPLICAS"); const int r = e ? atoi(e) : K4_REPLICAS; a.n_replicas = r < 1 ? 1 : r > K4_REPLICAS ? K4_REPLICAS : r; }
+    if (!any_gw || a.aggregate == 0) a.n_replicas = 1;
+    { const char *e = getenv("MULUT_K4_MERGE"); a.merge = e ? atoi(e) != 0 : 1; }
+    if (a.n_replicas > 1) {
+        replica_zero_kernel<<<(unsigned)sm_count() * 4, 256, 0, st>>>(a);
+        MULUT_CUDA(cudaGetLastError());
+    }
     switch (up) {
     case 1: stage_bwd_kernel<1><<<(unsigned)blocks, K4_T * K4_T, 0, st>>>(a, d_grad_out, d_mask, d_grad_x); break;
     case 2: stage_bwd_kernel<2><<<(unsigned)blocks, K4_T * K4_T, 0, st>>>(a, d_grad_out, d_mask, d_grad_x); break;
@@ -823,6 +1036,10 @@ extern "C" int mulut_stage_bwd_f32(const float *const *d_weights, int n_modes, c
     default: stage_bwd_kernel<4><<<(unsigned)blocks, K4_T * K4_T, 0, st>>>(a, d_grad_out, d_mask, d_grad_x); break;
     }
     MULUT_CUDA(cudaGetLastError());
+    if (a.n_replicas > 1) {
+        replica_sum_kernel<<<(unsigned)sm_count() * 4, 256, 0, st>>>(a, up * up);
+        MULUT_CUDA(cudaGetLastError());
+    }
     return MULUT_OK;
 }
 

@@ -323,7 +323,9 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     import ctypes
     from mulut_b200 import _lib
     L = _lib.lib()
-    assert L.mulut_stage_workspace_bytes(3, 83521, 4) == 3 * (83521 * 16 + ((83521 * 2 + 15) // 16) * 16) + 16
+    # quantised rows + clamp flags per mode, the statistics tail, three scratch copies of the gradient tables
+    assert L.mulut_stage_workspace_bytes(3, 83521, 4) == (3 * (83521 * 16 + ((83521 * 2 + 15) // 16) * 16) + 16 +
+                                                          3 * 3 * 83521 * 16 * 4)
     assert L.mulut_stage_workspace_bytes(3, 83521, 1) > 0 and L.mulut_stage_workspace_bytes(0, 83521, 4) == 0
     one = ctypes.c_void_p(16)                  # a non-null, 16-byte aligned dummy: never dereferenced on these paths
     ptrs = (ctypes.c_void_p * 1)(16)

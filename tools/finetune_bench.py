@@ -72,7 +72,7 @@ def _time_graph(g, steps, warmup, world, dist, dev):
 
 
 def finetune_block(rank, world, local, dist=None, steps=30, warmup=10, batch=256, crop=48, smooth=False,
-                   reference_fn=None, clock_sampler=None):
+                   reference_fn=None, clock_sampler=None, phases_wanted=True):
     """reference_fn(luts, batch, crop, dev, steps) -> dict: the reference-module leg (bench.py owns it: it runs code
     staged under oracle/_ref, and only bench.py's baseline legs may execute the oracle tree)."""
     import torch
@@ -101,6 +101,10 @@ def finetune_block(rank, world, local, dist=None, steps=30, warmup=10, batch=256
     loss = float(gs.loss.item())
     clocks = sampler.stop() if sampler else None
 
+    if not phases_wanted:
+        return {"workload": "the same step on low-frequency patches (neighbouring pixels share LUT rows, like natural "
+                            "images: the LUT-gradient atomics collide on a few hundred hot rows)",
+                "ms_per_step": ms_full, "patches_per_s": batch / (ms_full * 1e-3), "loss": loss}, gs
     # ---- the phases, each as its own graph (same buffers, same kernels); the step itself starts the all-reduce of
     # the last stage's tables under the first stage's backward (GraphedStep), the phases are timed one after another ----
     overlapped = gs.model._stage_grads_cb is not None
