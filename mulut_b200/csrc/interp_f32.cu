@@ -638,17 +638,21 @@ constexpr int K4P_ROWS = 9 * K4P_SLAB;           // one half: slabs 0..8 or 8..1
 constexpr int K4P_THREADS = 768;
 constexpr int K4P_WARPS = K4P_THREADS / 32;
 constexpr int K4P_RING = 64;                     // per-warp queue of pixel indices (< 32 left + 32 appended)
-constexpr size_t K4P_SMEM = (size_t)(K4P_ROWS + 3) / 4 * 16 + (size_t)K4P_WARPS * K4P_RING * 4;
+constexpr int K4P_FLAG_WORDS = (K4P_ROWS + 31) / 32;   // the half's clamp flags as a bitmap (5.5 KB): 20 random 2-byte
+                                                        // global gathers per pixel otherwise - they were half the kernel
+constexpr size_t K4P_TAB_BYTES = (size_t)(K4P_ROWS + 3) / 4 * 16;
+constexpr size_t K4P_RING_BYTES = (size_t)K4P_WARPS * K4P_RING * 4;
+constexpr size_t K4P_SMEM = K4P_TAB_BYTES + K4P_RING_BYTES + (size_t)K4P_FLAG_WORDS * 4;
 
 template <bool AGG>
 __device__ __forceinline__ void private_bwd_pixel(const StageF32Args &a, int m, int half_base, size_t p, float g,
-                                                  unsigned active, float *__restrict__ s_tab)
+                                                  unsigned active, float *__restrict__ s_tab,
+                                                  const uint32_t *__restrict__ s_flag)
 {
     const int x = (int)(p % a.w);
     const size_t rr = p / a.w;
     const int y = (int)(rr % a.h);
     const float *__restrict__ plane = a.x + (rr / a.h) * (size_t)a.h * a.w;
-    const uint16_t *__restrict__ FL = a.wflag[m];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         float t[4];
@@ -662,9 +666,9 @@ __device__ __forceinline__ void private_bwd_pixel(const StageF32Args &a, int m, 
         simplex_from_taps(t, 4, a.n_rows, s);
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            float c[1];
-            c[0] = (__ldg(FL + s.v[k]) & 1u) ? 127.f * (s.w[k] * g) : 0.f;     // same product as stage_bwd_body
             const int rel = min(max(s.v[k] - half_base, 0), K4P_ROWS - 1);      // in range for inputs 0..255
+            float c[1];
+            c[0] = ((s_flag[rel >> 5] >> (rel & 31)) & 1u) ? 127.f * (s.w[k] * g) : 0.f;   // same product as stage_bwd_body
             bool live = s.w[k] != 0.f;
             if (AGG) live = warp_merge_rows<1>(active, live ? rel : -1 - (int)(threadIdx.x & 31), c) && live;
             if (live && c[0] != 0.f) atomicAdd(s_tab + rel, c[0]);
@@ -674,7 +678,8 @@ __device__ __forceinline__ void private_bwd_pixel(const StageF32Args &a, int m, 
 
 template <bool AGG>
 __device__ __forceinline__ void private_bwd_body(const StageF32Args &a, const float *__restrict__ gout,
-                                                 const uint8_t *__restrict__ mask, float *s_tab, uint32_t *s_ring)
+                                                 const uint8_t *__restrict__ mask, float *s_tab, uint32_t *s_ring,
+                                                 uint32_t *s_flag)
 {
     const int kinds = 2 * a.n_modes;
     const int kind = blockIdx.x % kinds, slot = blockIdx.x / kinds;
@@ -685,6 +690,23 @@ __device__ __forceinline__ void private_bwd_body(const StageF32Args &a, const fl
     const size_t total = (size_t)a.BC * a.h * a.w;
     const float inv_q = 1.f / 16.f;
     for (int i = threadIdx.x; i < (K4P_ROWS + 3) / 4 * 4; i += blockDim.x) s_tab[i] = 0.f;
+    {
+        const uint16_t *__restrict__ FL = a.wflag[m] + half_base;
+        constexpr int U = 8;                                                 // bitmap words per warp pass: 8 loads in flight
+        for (int w0 = warp * U; w0 < K4P_FLAG_WORDS; w0 += K4P_WARPS * U) {
+            uint32_t f[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int row = (w0 + u) * 32 + lane;
+                f[u] = row < K4P_ROWS ? (uint32_t)__ldg(FL + row) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned bits = __ballot_sync(0xffffffffu, (f[u] & 1u) != 0u);
+                if (lane == 0 && w0 + u < K4P_FLAG_WORDS) s_flag[w0 + u] = bits;
+            }
+        }
+    }
     __syncthreads();
 
     uint32_t *ring = s_ring + warp * K4P_RING;
@@ -705,7 +727,7 @@ __device__ __forceinline__ void private_bwd_body(const StageF32Args &a, const fl
         if (qn >= 32) {
             const size_t pp = ring[(head + lane) & (K4P_RING - 1)];
             const float g = __fdiv_rn(__ldg(gout + pp), a.avg) * inv_q;
-            private_bwd_pixel<AGG>(a, m, half_base, pp, g, 0xffffffffu, s_tab);
+            private_bwd_pixel<AGG>(a, m, half_base, pp, g, 0xffffffffu, s_tab, s_flag);
             head = (head + 32) & (K4P_RING - 1);
             qn -= 32;
             __syncwarp();
@@ -716,7 +738,7 @@ __device__ __forceinline__ void private_bwd_body(const StageF32Args &a, const fl
         if (lane < qn) {
             const size_t pp = ring[(head + lane) & (K4P_RING - 1)];
             const float g = __fdiv_rn(__ldg(gout + pp), a.avg) * inv_q;
-            private_bwd_pixel<AGG>(a, m, half_base, pp, g, active, s_tab);
+            private_bwd_pixel<AGG>(a, m, half_base, pp, g, active, s_tab, s_flag);
         }
     }
     __syncthreads();
@@ -738,10 +760,11 @@ stage1_bwd_private_kernel(const __grid_constant__ StageF32Args a, const float *_
 {
     extern __shared__ __align__(16) unsigned char k4p_smem[];
     float *s_tab = reinterpret_cast<float *>(k4p_smem);
-    uint32_t *s_ring = reinterpret_cast<uint32_t *>(k4p_smem + (size_t)(K4P_ROWS + 3) / 4 * 16);
+    uint32_t *s_ring = reinterpret_cast<uint32_t *>(k4p_smem + K4P_TAB_BYTES);
+    uint32_t *s_flag = reinterpret_cast<uint32_t *>(k4p_smem + K4P_TAB_BYTES + K4P_RING_BYTES);
     // no warp merge here: lanes on one row retry their shared-memory CAS a few times, which costs less than the
     // match + shuffle tree (smooth patches: 278 us without, 477 us with; noise: 147 us)
-    private_bwd_body<false>(a, gout, mask, s_tab, s_ring);
+    private_bwd_body<false>(a, gout, mask, s_tab, s_ring, s_flag);
 }
 
 __device__ __forceinline__ bool stage_rows_are_hot(const StageF32Args &a)
