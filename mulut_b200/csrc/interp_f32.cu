@@ -627,10 +627,10 @@ stage_bwd_kernel(const __grid_constant__ StageF32Args a, const float *__restrict
 // the others slabs 8..16: 9 x 4913 floats = 177 KB, one SM's shared memory.  A persistent CTA serves ONE
 // (mode, half): its warps scan their share of the pixels, queue the ones of their half whose output gradient is
 // live (per-warp ring in shared memory, so the 32 lanes always work on 32 queued pixels), add the 4 x 5 vertex
-// contributions with shared-memory atomics (a CAS loop for fp32: the merge tree of the global kernel runs first
-// when the forward saw lanes sharing rows) and the CTA flushes its slab range once with 16-byte vector reds:
+// contributions with shared-memory atomics (a CAS loop for fp32; lanes on one row simply retry - the merge tree of
+// the global kernel costs more than it saves here) and the CTA flushes its slab range once with 16-byte vector reds:
 // 6.5 M floats per launch instead of 35 M scalar reds.  Used when the stage needs no input gradient (stage 1)
-// and there are enough pixels to pay for the flush (see use_private_bwd).  stage_bwd_kernel<1> 269 -> 147 us at batch
+// and there are enough pixels to pay for the flush (see use_private_bwd).  stage_bwd_kernel<1> 269 -> 117 us at batch
 // 256 on noise patches, 450 -> 278 us on smooth ones.
 // ---------------------------------------------------------------------------
 constexpr int K4P_SLAB = 17 * 17 * 17;           // rows per value of tap a at interval 4
