@@ -384,3 +384,37 @@ def test_paired_threshold_form_equals_sorted_simplex_weights():
             corner = corner | (1 << (o3[:, j] + 1))
     assert (w_ref.sum(1) == 16).all()
     assert (w_new == w_ref).all()
+
+
+def test_header_is_plain_c99():
+    """The drop-in boundary is a C ABI: include/mulut.h must compile as C (no C++ types in the signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(ROOT, "include", "mulut.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_private_backward_halves_cover_every_row_a_pixel_touches():
+    """K4p (interp_f32.cu) keeps slabs 0..8 or 8..16 of a x1 table in shared memory and deals the pixels by their
+    centre tap (< 128 / >= 128).  Whatever the other three taps are, all five vertices of the simplex must then
+    lie in that half - checked on the oracle's vertex arithmetic (oracle/mulut_oracle.py:simplex_vertices) for
+    every centre value at the extreme and at random neighbour values."""
+    from oracle import mulut_oracle as O
+    L = 17
+    slab, rows_half = L ** 3, 9 * L ** 3
+    rng = np.random.default_rng(0)
+    others = np.concatenate([np.array([[0, 0, 0], [255, 255, 255], [0, 255, 0], [255, 0, 255], [15, 16, 240]]),
+                             rng.integers(0, 256, (200, 3))])
+    for ta in range(256):
+        half_base = 8 * slab if ta >= 128 else 0
+        t = np.concatenate([np.full((len(others), 1), ta), others], axis=1).T        # (4, n)
+        verts, w, _ = O.simplex_vertices(t, 4)
+        assert verts.min() >= half_base and verts.max() < half_base + rows_half, ta
+        assert verts.max() < L ** 4 and (w.sum(axis=0) == 16).all()
+    # the extremes fill the halves exactly: the lower one ends on its last row, the upper one starts on its first
+    assert O.simplex_vertices(np.array([[127], [255], [255], [255]]), 4)[0].max() == rows_half - 1
+    assert O.simplex_vertices(np.array([[128], [0], [0], [0]]), 4)[0].min() == 8 * slab
